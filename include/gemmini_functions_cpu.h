@@ -1,0 +1,3 @@
+/* gemmini_functions_cpu.h -- forwarding header so reference callers that include "gemmini_functions_cpu.h" compile
+ * unchanged against libmaveric_b200.so; all declarations live in one place. */
+#include "maveric_slam_compat.h"

@@ -1,0 +1,3 @@
+/* local_feature_pool.h -- forwarding header so reference callers that include "local_feature_pool.h" compile
+ * unchanged against libmaveric_b200.so; all declarations live in one place. */
+#include "maveric_slam_compat.h"

@@ -1,0 +1,3 @@
+/* pnp_solver.h -- forwarding header so reference callers that include "pnp_solver.h" compile
+ * unchanged against libmaveric_b200.so; all declarations live in one place. */
+#include "maveric_slam_compat.h"

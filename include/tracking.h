@@ -1,0 +1,3 @@
+/* tracking.h -- forwarding header so reference callers that include "tracking.h" compile
+ * unchanged against libmaveric_b200.so; all declarations live in one place. */
+#include "maveric_slam_compat.h"

@@ -1,0 +1,743 @@
+// api.cu -- the C ABI of libmaveric_b200.so: context management, the legacy
+// reference-shaped symbols (include/maveric_slam_compat.h), the host-pointer `_ex`
+// forms and the whole-path sequence calls (include/maveric_b200.h).
+//
+// There is no CPU implementation of the hot path in this library: every compute entry
+// point needs a CUDA device and reports MV_ERR_NO_DEVICE (new API) or aborts with a
+// message on stderr (legacy void symbols) when there is none.
+#include "mv_common.cuh"
+#include "svd3.cuh"
+
+#include <math.h>
+#include <stdlib.h>
+
+#include <mutex>
+
+#include "../../include/maveric_slam_compat.h"
+
+void mv_host_recover_pose(const float E[3][3], float R1[3][3], float R2[3][3], float t[3]);
+
+// ------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------
+extern "C" const char* mv_status_str(mv_status s) {
+  switch (s) {
+    case MV_OK: return "ok";
+    case MV_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case MV_ERR_CUDA: return "CUDA error";
+    case MV_ERR_BAD_ARG: return "bad argument";
+    case MV_ERR_TOO_MANY_VALID: return "valid cells reached max_valid (top_N.c:91-94)";
+  }
+  return "unknown";
+}
+
+extern "C" mv_status mv_ctx_create(int device, mv_ctx** out) {
+  if (!out) return MV_ERR_BAD_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) {
+    cudaGetLastError();
+    return MV_ERR_NO_DEVICE;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) {
+    cudaGetLastError();
+    return MV_ERR_NO_DEVICE;  // kernels are sm_100a only
+  }
+  if (cudaSetDevice(device) != cudaSuccess) return MV_ERR_NO_DEVICE;
+  mv_ctx* c = new mv_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return MV_ERR_CUDA;
+  }
+  *out = c;
+  return MV_OK;
+}
+
+extern "C" void mv_ctx_destroy(mv_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
+  for (auto& kv : c->scratch) cudaFree(kv.second.first);
+  if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->own_stream) cudaStreamDestroy(c->stream);
+  cudaStreamDestroy(c->copy_stream);
+  delete c;
+}
+
+extern "C" mv_status mv_ctx_set_stream(mv_ctx* c, void* s) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return MV_OK;
+}
+
+extern "C" mv_status mv_ctx_sync(mv_ctx* c) {
+  if (!c) return MV_ERR_BAD_ARG;
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MV_OK;
+}
+
+extern "C" const char* mv_last_error(mv_ctx* c) { return c ? c->err : "null context"; }
+extern "C" unsigned long long mv_ctx_launch_count(mv_ctx* c) { return c ? c->launches : 0; }
+
+extern "C" mv_status mv_ctx_profile(mv_ctx* c, int enable) {
+  if (!c) return MV_ERR_BAD_ARG;
+  c->profile = enable != 0;
+  for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
+  c->pending.clear();
+  c->prof.clear();
+  return MV_OK;
+}
+
+extern "C" mv_status mv_ctx_profile_read(mv_ctx* c, const char* tag, double* avg_ms, int* launches) {
+  if (!c || !tag) return MV_ERR_BAD_ARG;
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  for (auto& ev : c->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev.beg, ev.end) == cudaSuccess) {
+      c->prof[ev.tag].ms += ms;
+      c->prof[ev.tag].launches += 1;
+    }
+    cudaEventDestroy(ev.beg);
+    cudaEventDestroy(ev.end);
+  }
+  c->pending.clear();
+  auto it = c->prof.find(tag);
+  if (avg_ms) *avg_ms = (it == c->prof.end() || it->second.launches == 0) ? 0.0 : it->second.ms / it->second.launches;
+  if (launches) *launches = it == c->prof.end() ? 0 : it->second.launches;
+  return MV_OK;
+}
+
+mv_status mv_scratch(mv_ctx* c, const char* name, size_t bytes, void** out) {
+  auto& slot = c->scratch[name];
+  if (slot.second < bytes) {
+    if (slot.first) {
+      MV_CUDA(c, cudaStreamSynchronize(c->stream));
+      MV_CUDA(c, cudaFree(slot.first));
+      slot.first = nullptr;
+      slot.second = 0;
+    }
+    size_t want = bytes + bytes / 8 + 256;
+    MV_CUDA(c, cudaMalloc(&slot.first, want));
+    slot.second = want;
+  }
+  *out = slot.first;
+  return MV_OK;
+}
+
+mv_status mv_pinned(mv_ctx* c, size_t bytes, void** out) {
+  if (c->pinned_bytes < bytes) {
+    if (c->pinned) { MV_CUDA(c, cudaFreeHost(c->pinned)); c->pinned = nullptr; c->pinned_bytes = 0; }
+    MV_CUDA(c, cudaMallocHost(&c->pinned, bytes + 4096));
+    c->pinned_bytes = bytes + 4096;
+  }
+  *out = c->pinned;
+  return MV_OK;
+}
+
+// process-global context behind the legacy void symbols
+static std::mutex g_mu;
+static mv_ctx* g_ctx = nullptr;
+
+static mv_ctx* legacy_ctx() {
+  if (!g_ctx) {
+    mv_status st = mv_ctx_create(0, &g_ctx);
+    if (st != MV_OK) {
+      fprintf(stderr, "libmaveric_b200: %s\n", mv_status_str(st));
+      abort();
+    }
+  }
+  return g_ctx;
+}
+
+static void legacy_check(mv_ctx* c, mv_status st, const char* what) {
+  if (st != MV_OK) {
+    fprintf(stderr, "libmaveric_b200: %s failed: %s (%s)\n", what, mv_status_str(st), mv_last_error(c));
+    abort();
+  }
+}
+
+#define H2D(ctx, dst, src, bytes) MV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (ctx)->stream))
+#define D2H(ctx, dst, src, bytes) MV_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (ctx)->stream))
+
+// ------------------------------------------------------------------------------------
+// detector: host-pointer forms
+// ------------------------------------------------------------------------------------
+static mv_status detect_one(mv_ctx* c, float scale, const int8_t* h_semi, int cells, int32_t** d_idx,
+                            float** d_prob, int32_t** d_nv) {
+  void *ds, *dsc, *di, *dp, *dn;
+  mv_status st;
+  if ((st = mv_scratch(c, "ex.semi", (size_t)cells * 65 + 16, &ds))) return st;
+  if ((st = mv_scratch(c, "ex.scale", 16, &dsc))) return st;
+  if ((st = mv_scratch(c, "ex.idx", sizeof(int32_t) * cells, &di))) return st;
+  if ((st = mv_scratch(c, "ex.prob", sizeof(float) * cells, &dp))) return st;
+  if ((st = mv_scratch(c, "ex.nv", 16, &dn))) return st;
+  H2D(c, ds, h_semi, (size_t)cells * 65);
+  H2D(c, dsc, &scale, sizeof(float));
+  if ((st = mv_softmax_batch(c, 1, cells, (const int8_t*)ds, (const float*)dsc, (int32_t*)di, (float*)dp,
+                             (int32_t*)dn)))
+    return st;
+  *d_idx = (int32_t*)di; *d_prob = (float*)dp; *d_nv = (int32_t*)dn;
+  return MV_OK;
+}
+
+extern "C" mv_status compute_softmax_ex(mv_ctx* c, float scale, const int8_t* h_semi, int cells,
+                                        int* num_valid, int* max_indices, float* probs) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (!h_semi || cells <= 0 || !max_indices || !probs) MV_BAD_ARG(c, "compute_softmax_ex");
+  int32_t *di, *dn; float* dp;
+  mv_status st = detect_one(c, scale, h_semi, cells, &di, &dp, &dn);
+  if (st) return st;
+  int nv = 0;
+  D2H(c, max_indices, di, sizeof(int32_t) * cells);
+  D2H(c, probs, dp, sizeof(float) * cells);
+  D2H(c, &nv, dn, sizeof(int));
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (num_valid) *num_valid += nv;  // top_N.c:159: accumulates into the caller's counter
+  return MV_OK;
+}
+
+extern "C" mv_status compute_top_N_ex(mv_ctx* c, float scale, const int8_t* h_semi, int cells, int N,
+                                      int max_valid, int* num_selected, int* N_patches, int* N_indices,
+                                      float* N_probs) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (!h_semi || cells <= 0 || N <= 0 || max_valid <= 0 || !num_selected || !N_patches || !N_indices || !N_probs)
+    MV_BAD_ARG(c, "compute_top_N_ex");
+  int32_t *di, *dn; float* dp;
+  mv_status st = detect_one(c, scale, h_semi, cells, &di, &dp, &dn);
+  if (st) return st;
+  void *qp, *qi, *qpr, *qc;
+  if ((st = mv_scratch(c, "ex.qp", sizeof(int32_t) * N, &qp))) return st;
+  if ((st = mv_scratch(c, "ex.qi", sizeof(int32_t) * N, &qi))) return st;
+  if ((st = mv_scratch(c, "ex.qpr", sizeof(float) * N, &qpr))) return st;
+  if ((st = mv_scratch(c, "ex.qc", 16, &qc))) return st;
+  int32_t* ov = (int32_t*)qc + 1;
+  if ((st = mv_top_n_batch(c, 1, cells, N, max_valid, di, dp, (int32_t*)qp, (int32_t*)qi, (float*)qpr,
+                           (int32_t*)qc, ov)))
+    return st;
+  int meta[2] = {0, 0};
+  D2H(c, meta, qc, sizeof(meta));
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  *num_selected = 0;
+  if (meta[1]) return MV_ERR_TOO_MANY_VALID;
+  *num_selected = meta[0];
+  if (meta[0] > 0) {
+    D2H(c, N_patches, qp, sizeof(int32_t) * meta[0]);
+    D2H(c, N_indices, qi, sizeof(int32_t) * meta[0]);
+    D2H(c, N_probs, qpr, sizeof(float) * meta[0]);
+    MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  }
+  return MV_OK;
+}
+
+// legacy shape: 1920 cells, 1000 valid (top_N.c:51,73,151)
+extern "C" void compute_softmax(float scale, int8_t semi[2400][65], int* num_valid, int* max_indices,
+                                float* probs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  mv_ctx* c = legacy_ctx();
+  legacy_check(c, compute_softmax_ex(c, scale, &semi[0][0], 1920, num_valid, max_indices, probs),
+               "compute_softmax");
+}
+
+extern "C" void compute_top_N(float scale, int8_t semi[2400][65], int N, int* num_selected, int* N_patches,
+                              int* N_indices, float* N_probs) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  mv_ctx* c = legacy_ctx();
+  mv_status st = compute_top_N_ex(c, scale, &semi[0][0], 1920, N, 1000, num_selected, N_patches, N_indices,
+                                  N_probs);
+  if (st == MV_ERR_TOO_MANY_VALID) {  // top_N.c:91-94
+    printf("Exceed max number of features!\n");
+    exit(1);
+  }
+  legacy_check(c, st, "compute_top_N");
+}
+
+// ------------------------------------------------------------------------------------
+// matcher: host-pointer form
+// ------------------------------------------------------------------------------------
+extern "C" mv_status mv_match_pair_host(mv_ctx* c, const mv_match_params* p, const int8_t* h_desc0,
+                                        const int8_t* h_desc1, const int* max_indices0, const float* probs0,
+                                        int num_queries, const int* patches1, const int* indices1,
+                                        float* points1, float* points2, int* num_matches, int* cell0,
+                                        float* score) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (!p || !h_desc0 || !h_desc1 || !max_indices0 || !probs0 || num_queries < 0 || !points1 || !points2 ||
+      !num_matches)
+    MV_BAD_ARG(c, "mv_match_pair_host");
+  const int cells = p->rows * p->cols;
+  const int top_n = num_queries > 0 ? num_queries : 1;
+  const int M = p->max_matches;
+  void *dd, *di, *dp, *qp, *qi, *qc, *mp, *mc, *mcell, *msc;
+  mv_status st;
+  if ((st = mv_scratch(c, "mp.desc", (size_t)2 * cells * 256, &dd))) return st;
+  if ((st = mv_scratch(c, "mp.idx", sizeof(int32_t) * 2 * cells, &di))) return st;
+  if ((st = mv_scratch(c, "mp.prob", sizeof(float) * 2 * cells, &dp))) return st;
+  if ((st = mv_scratch(c, "mp.qp", sizeof(int32_t) * 2 * top_n, &qp))) return st;
+  if ((st = mv_scratch(c, "mp.qi", sizeof(int32_t) * 2 * top_n, &qi))) return st;
+  if ((st = mv_scratch(c, "mp.qc", 16, &qc))) return st;
+  if ((st = mv_scratch(c, "mp.pts", sizeof(float) * 4 * M, &mp))) return st;
+  if ((st = mv_scratch(c, "mp.cnt", 16, &mc))) return st;
+  if ((st = mv_scratch(c, "mp.cell", sizeof(int32_t) * M, &mcell))) return st;
+  if ((st = mv_scratch(c, "mp.score", sizeof(float) * M, &msc))) return st;
+  H2D(c, dd, h_desc0, (size_t)cells * 256);
+  H2D(c, (int8_t*)dd + (size_t)cells * 256, h_desc1, (size_t)cells * 256);
+  H2D(c, di, max_indices0, sizeof(int32_t) * cells);
+  H2D(c, dp, probs0, sizeof(float) * cells);
+  if (num_queries > 0) {
+    H2D(c, (int32_t*)qp + top_n, patches1, sizeof(int32_t) * num_queries);
+    H2D(c, (int32_t*)qi + top_n, indices1, sizeof(int32_t) * num_queries);
+  }
+  const int counts[2] = {0, num_queries};
+  H2D(c, qc, counts, sizeof(counts));
+  if ((st = mv_match_batch(c, p, 2, 1, top_n, nullptr, nullptr, (const int8_t*)dd, (const int32_t*)di,
+                           (const float*)dp, (const int32_t*)qp, (const int32_t*)qi, (const int32_t*)qc,
+                           (float*)mp, (int32_t*)mc, (int32_t*)mcell, nullptr, (float*)msc)))
+    return st;
+  int n = 0;
+  D2H(c, &n, mc, sizeof(int));
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  *num_matches = n;
+  if (n > 0) {
+    void* hp;
+    if ((st = mv_pinned(c, sizeof(float) * 4 * n, &hp))) return st;
+    D2H(c, hp, mp, sizeof(float) * 4 * n);
+    if (cell0) D2H(c, cell0, mcell, sizeof(int32_t) * n);
+    if (score) D2H(c, score, msc, sizeof(float) * n);
+    MV_CUDA(c, cudaStreamSynchronize(c->stream));
+    const float* v = (const float*)hp;
+    for (int i = 0; i < n; i++) {  // tracking_main.c:182-185: points1 = frame 0, points2 = frame 1
+      points1[2 * i] = v[4 * i]; points1[2 * i + 1] = v[4 * i + 1];
+      points2[2 * i] = v[4 * i + 2]; points2[2 * i + 1] = v[4 * i + 3];
+    }
+  }
+  return MV_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// legacy pose symbols (pnp_solver.h)
+// ------------------------------------------------------------------------------------
+extern "C" void normalize_points(const int num_points, const float points[][2], const float K[3][3],
+                                 float normalized_points[][2]) {
+  for (int i = 0; i < num_points; ++i) {  // pnp_solver.c:28-34
+    normalized_points[i][0] = mvsvd::fdiv(mvsvd::fsub(points[i][0], K[0][2]), K[0][0]);
+    normalized_points[i][1] = mvsvd::fdiv(mvsvd::fsub(points[i][1], K[1][2]), K[1][1]);
+  }
+}
+
+extern "C" void compute_essential_matrix(const int, const float[][2], const float[][2], float E[3][3]) {
+  // pnp_solver.c:36-86: the 8-point system is built and ignored; the result is I.
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) E[i][j] = i == j ? 1.0f : 0.0f;
+}
+
+extern "C" float compute_reprojection_error(const float p1[2], const float p2[2], const float E[3][3]) {
+  return mvsvd::reproj_error(p1[0], p1[1], p2[0], p2[1], E);
+}
+
+extern "C" void recover_pose_from_essential_matrix(float E[3][3], float R1[3][3], float R2[3][3], float t[3]) {
+  mv_host_recover_pose(E, R1, R2, t);
+}
+
+extern "C" void ransac_essential_matrix(const int num_points, const float points1[][2],
+                                        const float points2[][2], const float K[3][3],
+                                        const int num_iterations, const float inlier_threshold,
+                                        float best_E[3][3], int* best_inliers, int* num_inliers) {
+  (void)K;
+  std::lock_guard<std::mutex> lk(g_mu);
+  mv_ctx* c = legacy_ctx();
+  // Defined result where the reference has none (no match / no inlier).
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) best_E[i][j] = i == j ? 1.0f : 0.0f;
+  *num_inliers = 0;
+  if (num_points <= 0) return;
+  void *hp, *dp, *dc, *dn, *di;
+  legacy_check(c, mv_pinned(c, sizeof(float) * 4 * num_points, &hp), "ransac");
+  float* v = (float*)hp;
+  for (int i = 0; i < num_points; i++) {
+    v[4 * i] = points1[i][0]; v[4 * i + 1] = points1[i][1];
+    v[4 * i + 2] = points2[i][0]; v[4 * i + 3] = points2[i][1];
+  }
+  legacy_check(c, mv_scratch(c, "rs.pts", sizeof(float) * 4 * num_points, &dp), "ransac");
+  legacy_check(c, mv_scratch(c, "rs.cnt", 16, &dc), "ransac");
+  legacy_check(c, mv_scratch(c, "rs.ninl", 16, &dn), "ransac");
+  legacy_check(c, mv_scratch(c, "rs.inl", sizeof(int32_t) * num_points, &di), "ransac");
+  auto run = [&]() -> mv_status {
+    H2D(c, dp, hp, sizeof(float) * 4 * num_points);
+    H2D(c, dc, &num_points, sizeof(int));
+    mv_status st = mv_ransac_identity_batch(c, 1, num_points, (const float*)dp, (const int32_t*)dc,
+                                            num_iterations, inlier_threshold, (int32_t*)dn, (int32_t*)di,
+                                            nullptr);
+    if (st) return st;
+    int n = 0;
+    D2H(c, &n, dn, sizeof(int));
+    MV_CUDA(c, cudaStreamSynchronize(c->stream));
+    *num_inliers = n;
+    if (n > 0 && best_inliers) {
+      D2H(c, best_inliers, di, sizeof(int32_t) * n);
+      MV_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    return MV_OK;
+  };
+  legacy_check(c, run(), "ransac_essential_matrix");
+}
+
+// ------------------------------------------------------------------------------------
+// geometry PODs / projection factor (types.c, projection_factor.c): scalar helpers
+// ------------------------------------------------------------------------------------
+using mvsvd::fadd; using mvsvd::fmul; using mvsvd::fsub; using mvsvd::fdiv;
+
+extern "C" Vector2f add_Vector2f(Vector2f a, Vector2f b, float s) {
+  Vector2f v; v.x = fadd(a.x, fmul(s, b.x)); v.y = fadd(a.y, fmul(s, b.y)); return v;
+}
+extern "C" Vector3f add_Vector3f(Vector3f a, Vector3f b, float s) {
+  Vector3f v; v.x = fadd(a.x, fmul(s, b.x)); v.y = fadd(a.y, fmul(s, b.y)); v.z = fadd(a.z, fmul(s, b.z)); return v;
+}
+extern "C" Quaternionf mult_Quaternionf(Quaternionf a, Quaternionf b) {
+  Quaternionf q;  // types.c:18-25, left-to-right sums
+  q.w = fsub(fsub(fsub(fmul(a.w, b.w), fmul(a.x, b.x)), fmul(a.y, b.y)), fmul(a.z, b.z));
+  q.x = fsub(fadd(fadd(fmul(a.w, b.x), fmul(a.x, b.w)), fmul(a.y, b.z)), fmul(a.z, b.y));
+  q.y = fadd(fadd(fsub(fmul(a.w, b.y), fmul(a.x, b.z)), fmul(a.y, b.w)), fmul(a.z, b.x));
+  q.z = fadd(fsub(fadd(fmul(a.w, b.z), fmul(a.x, b.y)), fmul(a.y, b.x)), fmul(a.z, b.w));
+  return q;
+}
+extern "C" Quaternionf create_Quaternionf(float w, float x, float y, float z) {
+  Quaternionf q; q.w = w; q.x = x; q.y = y; q.z = z; return q;
+}
+extern "C" Quaternionf Quaternionf_from_Vector3f(Vector3f v) { return create_Quaternionf(0.0f, v.x, v.y, v.z); }
+extern "C" Quaternionf conjugate_Quaternionf(Quaternionf q) { return create_Quaternionf(q.w, -q.x, -q.y, -q.z); }
+extern "C" Vector3f Vector3f_from_Quaternionf(Quaternionf q) { Vector3f v; v.x = q.x; v.y = q.y; v.z = q.z; return v; }
+extern "C" Vector3f apply_rotation(Quaternionf q, Vector3f v) {
+  return Vector3f_from_Quaternionf(
+      mult_Quaternionf(mult_Quaternionf(q, Quaternionf_from_Vector3f(v)), conjugate_Quaternionf(q)));
+}
+extern "C" Vector3f apply_transform(SE3 T, Vector3f v) { return add_Vector3f(apply_rotation(T.q, v), T.t, 1.0f); }
+
+extern "C" ProjectionFactor* create_ProjectionFactor(Vector3f* landmark, SE3* pose, Vector2f measurement,
+                                                     Camera camera) {
+  ProjectionFactor* f = (ProjectionFactor*)malloc(sizeof(ProjectionFactor));  // caller frees
+  f->landmark = landmark; f->pose = pose; f->measurement = measurement; f->camera = camera;
+  return f;
+}
+extern "C" Vector2f project2d(const Vector3f p) { Vector2f r; r.x = fdiv(p.x, p.z); r.y = fdiv(p.y, p.z); return r; }
+extern "C" Vector2f cam_project(const Vector3f p, const Camera cam) {
+  Vector2f n = project2d(p), r;
+  r.x = fadd(fmul(n.x, cam.fx), cam.cx);
+  r.y = fadd(fmul(n.y, cam.fy), cam.cy);
+  return r;
+}
+extern "C" void compute_error_ProjectionFactor(ProjectionFactor* f) {
+  f->error = add_Vector2f(cam_project(apply_transform(*f->pose, *f->landmark), f->camera), f->measurement, -1.0f);
+}
+
+extern "C" void frame_create(const int rows, const int cols, const int channels, const char* data,
+                             const int feature_rows, const int feature_cols, const float semi_scale,
+                             const int8_t* semi, const float desc_scale, const int8_t* desc, Frame* frame) {
+  frame->rows = rows; frame->cols = cols; frame->channels = channels; frame->data = data;
+  frame->feature_rows = feature_rows; frame->feature_cols = feature_cols;
+  frame->semi_scale = semi_scale; frame->semi = semi;
+  frame->desc_scale = desc_scale; frame->desc = desc;
+}
+
+// ------------------------------------------------------------------------------------
+// matmul shim (gemmini_functions_cpu.h): one thread per C element, k sequential, in the
+// reference's operation order  c += ((sA*a)*sB)*b  (gemmini_functions_cpu.h:48,110)
+// ------------------------------------------------------------------------------------
+__global__ void matmul_shim_kernel(size_t I, size_t J, size_t K, const float* A, const float* B,
+                                   const float* D, float* C, size_t a_i, size_t a_k, size_t b_k, size_t b_j,
+                                   size_t sD, size_t sC, float as, float bs, float ds, int use_d) {
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= I * J) return;
+  const size_t i = idx / J, j = idx % J;
+  float c = use_d ? __fmul_rn(ds, D[i * sD + j]) : C[i * sC + j];
+  for (size_t k = 0; k < K; k++)
+    c = __fadd_rn(c, __fmul_rn(__fmul_rn(__fmul_rn(as, A[i * a_i + k * a_k]), bs), B[k * b_k + j * b_j]));
+  C[i * sC + j] = c;
+}
+
+static mv_status matmul_host(mv_ctx* c, size_t I, size_t J, size_t K, const float* A, const float* B,
+                             const float* D, float* C, size_t sA, size_t sB, size_t sD, size_t sC, float as,
+                             float bs, float ds, bool tA, bool tB) {
+  if (I == 0 || J == 0) return MV_OK;
+  const size_t nA = K == 0 ? 0 : (tA ? (K - 1) * sA + I : (I - 1) * sA + K);
+  const size_t nB = K == 0 ? 0 : (tB ? (J - 1) * sB + K : (K - 1) * sB + J);
+  const size_t nC = (I - 1) * sC + J;
+  const size_t nD = D ? (I - 1) * sD + J : 0;
+  void *dA, *dB, *dC, *dD = nullptr;
+  mv_status st;
+  if ((st = mv_scratch(c, "mm.A", sizeof(float) * (nA + 1), &dA))) return st;
+  if ((st = mv_scratch(c, "mm.B", sizeof(float) * (nB + 1), &dB))) return st;
+  if ((st = mv_scratch(c, "mm.C", sizeof(float) * nC, &dC))) return st;
+  if (nA) H2D(c, dA, A, sizeof(float) * nA);
+  if (nB) H2D(c, dB, B, sizeof(float) * nB);
+  H2D(c, dC, C, sizeof(float) * nC);
+  if (D) {
+    if (D == C && sD == sC) {
+      dD = dC;  // in-place form used by local_bundle_adjustment.c:232-245
+    } else {
+      if ((st = mv_scratch(c, "mm.D", sizeof(float) * nD, &dD))) return st;
+      H2D(c, dD, D, sizeof(float) * nD);
+    }
+  }
+  const size_t total = I * J;
+  matmul_shim_kernel<<<(unsigned)((total + 127) / 128), 128, 0, c->stream>>>(
+      I, J, K, (const float*)dA, (const float*)dB, (const float*)dD, (float*)dC, tA ? 1 : sA, tA ? sA : 1,
+      tB ? 1 : sB, tB ? sB : 1, sD, sC, as, bs, ds, D ? 1 : 0);
+  MV_CHECK_LAUNCH(c);
+  D2H(c, C, dC, sizeof(float) * nC);
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  return MV_OK;
+}
+
+extern "C" void matmul(size_t dim_I, size_t dim_J, size_t dim_K, const elem_t* A, const elem_t* B, elem_t* C,
+                       size_t stride_A, size_t stride_B, size_t stride_C, scale_t A_scale_factor,
+                       scale_t B_scale_factor, bool transpose_A, bool transpose_B) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  mv_ctx* c = legacy_ctx();
+  legacy_check(c, matmul_host(c, dim_I, dim_J, dim_K, A, B, nullptr, C, stride_A, stride_B, 0, stride_C,
+                              A_scale_factor, B_scale_factor, 0.0f, transpose_A, transpose_B), "matmul");
+}
+
+extern "C" void matmul2(size_t dim_I, size_t dim_J, size_t dim_K, const elem_t* A, const elem_t* B,
+                        const elem_t* D, elem_t* C, size_t stride_A, size_t stride_B, size_t stride_D,
+                        size_t stride_C, scale_t A_scale_factor, scale_t B_scale_factor,
+                        scale_t D_scale_factor, bool transpose_A, bool transpose_B) {
+  std::lock_guard<std::mutex> lk(g_mu);
+  mv_ctx* c = legacy_ctx();
+  legacy_check(c, matmul_host(c, dim_I, dim_J, dim_K, A, B, D, C, stride_A, stride_B, stride_D, stride_C,
+                              A_scale_factor, B_scale_factor, D_scale_factor, transpose_A, transpose_B),
+               "matmul2");
+}
+
+// ------------------------------------------------------------------------------------
+// whole path over a sequence
+// ------------------------------------------------------------------------------------
+extern "C" void mv_track_params_default(mv_track_params* p, int rows, int cols) {
+  memset(p, 0, sizeof(*p));
+  mv_match_params_default(&p->match, rows, cols);
+  mv_pnp_params_default(&p->pnp);
+  p->top_n = 100;            // tracking_main.c:14
+  p->max_valid = 1000;       // top_N.c:51
+  p->ransac_iterations = 10; // tracking_main.c:210
+  p->ransac_threshold = 1.1f;
+}
+
+__global__ void pack_results_kernel(int n_pairs, const float* __restrict__ pose, const float* __restrict__ stats,
+                                    const int32_t* __restrict__ match_count,
+                                    const int32_t* __restrict__ ransac_inliers,
+                                    const int32_t* __restrict__ overflow, mv_pair_result* __restrict__ out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pairs) return;
+  mv_pair_result r;
+  for (int i = 0; i < 4; i++) r.q[i] = pose[(size_t)p * 7 + i];
+  for (int i = 0; i < 3; i++) r.t[i] = pose[(size_t)p * 7 + 4 + i];
+  r.pnp_inliers = stats[(size_t)p * 4 + 0];
+  r.pnp_cost = stats[(size_t)p * 4 + 1];
+  r.best_hypothesis = (int)stats[(size_t)p * 4 + 2];
+  r.num_matches = match_count[p];
+  r.ransac_inliers = ransac_inliers ? ransac_inliers[p] : 0;
+  r.status = (overflow[p] || overflow[p + 1]) ? (int)MV_ERR_TOO_MANY_VALID : 0;
+  r.pad[0] = r.pad[1] = r.pad[2] = 0;
+  out[p] = r;
+}
+
+static mv_status track_sequence_on(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
+                                   const float* d_semi_scale, const int8_t* d_desc, const float* d_depth,
+                                   mv_pair_result* d_results, const char* ns) {
+  const int cells = p->match.rows * p->match.cols;
+  const int n_pairs = n_frames - 1;
+  const int N = p->top_n, M = p->match.max_matches;
+  std::string s(ns);
+  void *idx, *prob, *qp, *qi, *qpr, *qc, *ov, *mp, *mc, *mcell, *rin, *corr, *pose, *stats;
+  mv_status st;
+#define SCR(var, name, bytes) if ((st = mv_scratch(c, (s + name).c_str(), (bytes), &var))) return st
+  SCR(idx, ".idx", sizeof(int32_t) * (size_t)n_frames * cells);
+  SCR(prob, ".prob", sizeof(float) * (size_t)n_frames * cells);
+  SCR(qp, ".qp", sizeof(int32_t) * (size_t)n_frames * N);
+  SCR(qi, ".qi", sizeof(int32_t) * (size_t)n_frames * N);
+  SCR(qpr, ".qpr", sizeof(float) * (size_t)n_frames * N);
+  SCR(qc, ".qc", sizeof(int32_t) * (size_t)n_frames);
+  SCR(ov, ".ov", sizeof(int32_t) * (size_t)n_frames);
+  SCR(mp, ".mp", sizeof(float) * 4 * (size_t)n_pairs * M);
+  SCR(mc, ".mc", sizeof(int32_t) * (size_t)n_pairs);
+  SCR(mcell, ".mcell", sizeof(int32_t) * (size_t)n_pairs * M);
+  SCR(rin, ".rin", sizeof(int32_t) * (size_t)n_pairs);
+  SCR(corr, ".corr", sizeof(float) * 5 * (size_t)n_pairs * M);
+  SCR(pose, ".pose", sizeof(float) * 7 * (size_t)n_pairs);
+  SCR(stats, ".stats", sizeof(float) * 4 * (size_t)n_pairs);
+#undef SCR
+  if ((st = mv_softmax_batch(c, n_frames, cells, d_semi, d_semi_scale, (int32_t*)idx, (float*)prob, nullptr)))
+    return st;
+  if ((st = mv_top_n_batch(c, n_frames, cells, N, p->max_valid, (const int32_t*)idx, (const float*)prob,
+                           (int32_t*)qp, (int32_t*)qi, (float*)qpr, (int32_t*)qc, (int32_t*)ov)))
+    return st;
+  if ((st = mv_match_batch(c, &p->match, n_frames, n_pairs, N, nullptr, nullptr, d_desc, (const int32_t*)idx,
+                           (const float*)prob, (const int32_t*)qp, (const int32_t*)qi, (const int32_t*)qc,
+                           (float*)mp, (int32_t*)mc, (int32_t*)mcell, nullptr, nullptr)))
+    return st;
+  if (p->ransac_iterations > 0) {
+    if ((st = mv_ransac_identity_batch(c, n_pairs, M, (const float*)mp, (const int32_t*)mc,
+                                       p->ransac_iterations, p->ransac_threshold, (int32_t*)rin, nullptr,
+                                       nullptr)))
+      return st;
+  }
+  if ((st = mv_build_corr_batch(c, n_pairs, cells, p->match.rows, M, nullptr, d_depth, p->pnp.fx, p->pnp.fy,
+                                p->pnp.cx, p->pnp.cy, (const float*)mp, (const int32_t*)mc,
+                                (const int32_t*)mcell, (float*)corr)))
+    return st;
+  if ((st = mv_pnp_gn_batch(c, &p->pnp, n_pairs, M, (const float*)corr, (const int32_t*)mc, nullptr,
+                            (float*)pose, (float*)stats, nullptr)))
+    return st;
+  pack_results_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(
+      n_pairs, (const float*)pose, (const float*)stats, (const int32_t*)mc,
+      p->ransac_iterations > 0 ? (const int32_t*)rin : nullptr, (const int32_t*)ov, d_results);
+  MV_CHECK_LAUNCH(c);
+  return MV_OK;
+}
+
+extern "C" mv_status mv_track_sequence(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
+                                       const float* d_semi_scale, const int8_t* d_desc, const float* d_depth,
+                                       mv_pair_result* d_results) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (!p || n_frames < 2 || !d_semi || !d_semi_scale || !d_desc || !d_depth || !d_results)
+    MV_BAD_ARG(c, "mv_track_sequence");
+  return track_sequence_on(c, p, n_frames, d_semi, d_semi_scale, d_desc, d_depth, d_results, "seq");
+}
+
+// Host inputs: chunks of frames are staged on the copy stream into one of two device
+// buffers while the previous chunk computes; consecutive chunks share one halo frame.
+extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p, int n_frames,
+                                            const int8_t* h_semi, const float* h_semi_scale,
+                                            const int8_t* h_desc, const float* h_depth,
+                                            mv_pair_result* h_results, unsigned long long* h2d_bytes,
+                                            unsigned long long* d2h_bytes) {
+  if (!c) return MV_ERR_BAD_ARG;
+  if (!p || n_frames < 2 || !h_semi || !h_semi_scale || !h_desc || !h_depth || !h_results)
+    MV_BAD_ARG(c, "mv_track_sequence_host");
+  const int cells = p->match.rows * p->match.cols;
+  const int n_pairs = n_frames - 1;
+  const size_t frame_bytes = (size_t)cells * (65 + 256 + 4) + 4;
+  // chunk size: about 512 MB of frames per buffer, at least 8 pairs
+  int chunk_pairs = (int)((512ull << 20) / frame_bytes);
+  if (chunk_pairs < 8) chunk_pairs = 8;
+  if (chunk_pairs > n_pairs) chunk_pairs = n_pairs;
+  const int cf = chunk_pairs + 1;
+  void *bs[2], *bd[2], *bz[2], *bsc[2], *dres;
+  mv_status st;
+  const size_t semi_pad = ((size_t)cf * cells * 65 + 255) & ~(size_t)255;
+  for (int b = 0; b < 2; b++) {
+    const std::string n = "host.buf" + std::to_string(b);
+    if ((st = mv_scratch(c, (n + ".semi").c_str(), semi_pad, &bs[b]))) return st;
+    if ((st = mv_scratch(c, (n + ".desc").c_str(), (size_t)cf * cells * 256, &bd[b]))) return st;
+    if ((st = mv_scratch(c, (n + ".depth").c_str(), sizeof(float) * (size_t)cf * cells, &bz[b]))) return st;
+    if ((st = mv_scratch(c, (n + ".scale").c_str(), sizeof(float) * (size_t)cf, &bsc[b]))) return st;
+  }
+  if ((st = mv_scratch(c, "host.results", sizeof(mv_pair_result) * (size_t)n_pairs, &dres))) return st;
+  cudaEvent_t copied[2], consumed[2];
+  for (int b = 0; b < 2; b++) {
+    MV_CUDA(c, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    MV_CUDA(c, cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+  }
+  unsigned long long up = 0;
+  int b = 0;
+  for (int p0 = 0; p0 < n_pairs; p0 += chunk_pairs, b ^= 1) {
+    const int np = (n_pairs - p0) < chunk_pairs ? (n_pairs - p0) : chunk_pairs;
+    const int nf = np + 1;
+    // the copy engine may refill buffer b only after the compute that read it is done
+    MV_CUDA(c, cudaStreamWaitEvent(c->copy_stream, consumed[b], 0));
+    MV_CUDA(c, cudaMemcpyAsync(bs[b], h_semi + (size_t)p0 * cells * 65, (size_t)nf * cells * 65,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    MV_CUDA(c, cudaMemcpyAsync(bd[b], h_desc + (size_t)p0 * cells * 256, (size_t)nf * cells * 256,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    MV_CUDA(c, cudaMemcpyAsync(bz[b], h_depth + (size_t)p0 * cells, sizeof(float) * (size_t)nf * cells,
+                               cudaMemcpyHostToDevice, c->copy_stream));
+    MV_CUDA(c, cudaMemcpyAsync(bsc[b], h_semi_scale + p0, sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice,
+                               c->copy_stream));
+    up += (unsigned long long)nf * ((size_t)cells * (65 + 256 + 4) + 4);
+    MV_CUDA(c, cudaEventRecord(copied[b], c->copy_stream));
+    MV_CUDA(c, cudaStreamWaitEvent(c->stream, copied[b], 0));
+    if ((st = track_sequence_on(c, p, nf, (const int8_t*)bs[b], (const float*)bsc[b], (const int8_t*)bd[b],
+                                (const float*)bz[b], (mv_pair_result*)dres + p0, "hseq")))
+      return st;
+    MV_CUDA(c, cudaEventRecord(consumed[b], c->stream));
+  }
+  MV_CUDA(c, cudaMemcpyAsync(h_results, dres, sizeof(mv_pair_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
+                             c->stream));
+  MV_CUDA(c, cudaStreamSynchronize(c->stream));
+  MV_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  for (int i = 0; i < 2; i++) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
+  if (h2d_bytes) *h2d_bytes = up;
+  if (d2h_bytes) *d2h_bytes = sizeof(mv_pair_result) * (unsigned long long)n_pairs;
+  return MV_OK;
+}
+
+// ------------------------------------------------------------------------------------
+// track() (tracking.h:3) with the semantics of tracking_main.c:84-218
+// ------------------------------------------------------------------------------------
+static void rot_to_quat(const float R[3][3], Quaternionf* q) {
+  const float tr = R[0][0] + R[1][1] + R[2][2];
+  if (tr > 0.0f) {
+    float s = sqrtf(tr + 1.0f) * 2.0f;
+    q->w = 0.25f * s; q->x = (R[2][1] - R[1][2]) / s; q->y = (R[0][2] - R[2][0]) / s; q->z = (R[1][0] - R[0][1]) / s;
+  } else if (R[0][0] > R[1][1] && R[0][0] > R[2][2]) {
+    float s = sqrtf(1.0f + R[0][0] - R[1][1] - R[2][2]) * 2.0f;
+    q->w = (R[2][1] - R[1][2]) / s; q->x = 0.25f * s; q->y = (R[0][1] + R[1][0]) / s; q->z = (R[0][2] + R[2][0]) / s;
+  } else if (R[1][1] > R[2][2]) {
+    float s = sqrtf(1.0f + R[1][1] - R[0][0] - R[2][2]) * 2.0f;
+    q->w = (R[0][2] - R[2][0]) / s; q->x = (R[0][1] + R[1][0]) / s; q->y = 0.25f * s; q->z = (R[1][2] + R[2][1]) / s;
+  } else {
+    float s = sqrtf(1.0f + R[2][2] - R[0][0] - R[1][1]) * 2.0f;
+    q->w = (R[1][0] - R[0][1]) / s; q->x = (R[0][2] + R[2][0]) / s; q->y = (R[1][2] + R[2][1]) / s; q->z = 0.25f * s;
+  }
+}
+
+extern "C" void track(const Frame* last_frame, const Frame* current_frame, const int x_shift,
+                      const int y_shift, const int window_size, const float threshold, SE3* transform) {
+  transform->q = create_Quaternionf(1.0f, 0.0f, 0.0f, 0.0f);
+  transform->t.x = transform->t.y = transform->t.z = 0.0f;
+  if (last_frame == NULL || current_frame == NULL) return;  // tracking.h:4-7
+  const int rows = current_frame->feature_rows, cols = current_frame->feature_cols;
+  const int cells = rows * cols;
+  const int N = 100, MAXM = 150;
+  mv_ctx* c;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    c = legacy_ctx();
+  }
+  int* idx0 = (int*)malloc(sizeof(int) * cells);
+  float* pr0 = (float*)malloc(sizeof(float) * cells);
+  int qp[N], qi[N]; float qpr[N];
+  int nv = 0, nq = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    legacy_check(c, compute_softmax_ex(c, last_frame->semi_scale, last_frame->semi, cells, &nv, idx0, pr0), "track");
+    mv_status st = compute_top_N_ex(c, current_frame->semi_scale, current_frame->semi, cells, N, 1000, &nq, qp, qi, qpr);
+    if (st == MV_ERR_TOO_MANY_VALID) { printf("Exceed max number of features!\n"); exit(1); }
+    legacy_check(c, st, "track");
+  }
+  mv_match_params mp;
+  mv_match_params_default(&mp, rows, cols);
+  mp.shift_x = x_shift; mp.shift_y = y_shift; mp.radius = (window_size - 1) / 2;  // tracking.h:20
+  mp.match_threshold = (double)threshold; mp.max_matches = MAXM;
+  float p1[MAXM][2], p2[MAXM][2];
+  int nm = 0;
+  {
+    std::lock_guard<std::mutex> lk(g_mu);
+    legacy_check(c, mv_match_pair_host(c, &mp, last_frame->desc, current_frame->desc, idx0, pr0, nq, qp, qi,
+                                       &p1[0][0], &p2[0][0], &nm, nullptr, nullptr), "track");
+  }
+  free(idx0); free(pr0);
+  float E[3][3], K[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  int inl[MAXM], ninl = 0;
+  ransac_essential_matrix(nm, p1, p2, K, 10, 1.1f, E, inl, &ninl);  // tracking_main.c:210-214
+  float R1[3][3], R2[3][3], t[3];
+  recover_pose_from_essential_matrix(E, R1, R2, t);                  // :218
+  rot_to_quat(R1, &transform->q);
+  transform->t.x = t[0]; transform->t.y = t[1]; transform->t.z = t[2];
+}

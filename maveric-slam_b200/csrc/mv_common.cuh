@@ -1,0 +1,121 @@
+// mv_common.cuh -- context, error plumbing and launch helpers shared by the kernels
+// of libmaveric_b200.so (sm_100a only; there is deliberately no host fallback).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/maveric_b200.h"
+
+struct mv_prof_slot {
+  double ms = 0.0;
+  int launches = 0;
+};
+
+struct mv_pending_event {
+  std::string tag;
+  cudaEvent_t beg, end;
+};
+
+struct mv_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;      // compute stream (owned unless set_stream)
+  bool own_stream = true;
+  cudaStream_t copy_stream = nullptr; // H2D staging for the host-buffer sequence call
+  char err[512] = {0};
+  unsigned long long launches = 0;
+  bool profile = false;
+  std::map<std::string, mv_prof_slot> prof;
+  std::vector<mv_pending_event> pending;
+
+  // scratch arena, grown on demand, never shrunk; owned by the context
+  std::map<std::string, std::pair<void*, size_t>> scratch;
+  // pinned host mirror for small synchronous host-pointer calls
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+};
+
+#define MV_CUDA(ctx, call)                                                          \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, \
+               #call, cudaGetErrorString(e__));                                     \
+      return MV_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define MV_CHECK_LAUNCH(ctx)                                                        \
+  do {                                                                              \
+    (ctx)->launches++;                                                              \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d launch -> %s", __FILE__,      \
+               __LINE__, cudaGetErrorString(e__));                                  \
+      return MV_ERR_CUDA;                                                           \
+    }                                                                               \
+  } while (0)
+
+#define MV_BAD_ARG(ctx, msg)                                              \
+  do {                                                                    \
+    snprintf((ctx)->err, sizeof((ctx)->err), "bad argument: %s", msg);    \
+    return MV_ERR_BAD_ARG;                                                \
+  } while (0)
+
+// Scoped per-tag device timing (CUDA events on the compute stream), on when the
+// context is in profile mode.  Results are folded in by mv_ctx_profile_read().
+struct mv_prof_scope {
+  mv_ctx* ctx;
+  mv_pending_event ev;
+  bool on;
+  mv_prof_scope(mv_ctx* c, const char* tag) : ctx(c), on(c->profile) {
+    if (!on) return;
+    ev.tag = tag;
+    cudaEventCreate(&ev.beg);
+    cudaEventCreate(&ev.end);
+    cudaEventRecord(ev.beg, ctx->stream);
+  }
+  ~mv_prof_scope() {
+    if (!on) return;
+    cudaEventRecord(ev.end, ctx->stream);
+    ctx->pending.push_back(ev);
+  }
+};
+
+mv_status mv_scratch(mv_ctx* ctx, const char* name, size_t bytes, void** out);
+mv_status mv_pinned(mv_ctx* ctx, size_t bytes, void** out);
+
+// float bounds that make a float-vs-double comparison exact in fp32:
+//   (double)s >  T  <=>  s >  mv_round_down(T)
+//   (double)s <  T  <=>  s <  mv_round_up(T)
+static inline float mv_round_down(double t) {
+  float f = (float)t;
+  if ((double)f > t) f = nextafterf(f, -INFINITY);
+  return f;
+}
+static inline float mv_round_up(double t) {
+  float f = (float)t;
+  if ((double)f < t) f = nextafterf(f, INFINITY);
+  return f;
+}
+
+// ---- counter-based random numbers (same as oracle/ and synth.py) ----
+__host__ __device__ static inline uint64_t mv_sm64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+__host__ __device__ static inline uint64_t mv_ctr(uint64_t mixed_seed, uint64_t tag, uint64_t a,
+                                                  uint64_t b, uint64_t c) {
+  return mv_sm64(mixed_seed + ((tag << 56) | ((a & 0xFFFFFFull) << 32) | ((b & 0xFFFFFFull) << 8) |
+                               (c & 0xFFull)));
+}
+

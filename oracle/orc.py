@@ -1,0 +1,251 @@
+"""ctypes bindings of the CPU checkers (TEST INFRASTRUCTURE ONLY).
+
+``T2``  = oracle/libmv_oracle.so, this repository's restatement (oracle/mv_oracle.c).
+``T1``  = oracle/_ref/libmaveric_ref.so, the reference's own sources compiled unmodified
+          from /root/reference by oracle/Makefile (prebuilt file travels to the GPU box).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_i8p = np.ctypeslib.ndpointer(np.int8, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(np.int32, flags="C_CONTIGUOUS")
+_f32p = np.ctypeslib.ndpointer(np.float32, flags="C_CONTIGUOUS")
+
+
+def build(force: bool = False) -> None:
+    need = force or not os.path.exists(os.path.join(_HERE, "libmv_oracle.so")) \
+        or os.path.getmtime(os.path.join(_HERE, "libmv_oracle.so")) < os.path.getmtime(os.path.join(_HERE, "mv_oracle.c"))
+    if need or (os.path.isdir("/root/reference/src") and not os.path.exists(os.path.join(_HERE, "_ref", "libmaveric_ref.so"))):
+        subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
+
+
+class MatchCfg(C.Structure):
+    _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("shift_x", C.c_int), ("shift_y", C.c_int),
+                ("radius", C.c_int), ("max_matches", C.c_int),
+                ("match_threshold", C.c_double), ("min_prob0", C.c_double)]
+
+
+class MatchStats(C.Structure):
+    _fields_ = [("window_cells", C.c_longlong), ("pairs_256", C.c_longlong), ("pairs_64", C.c_longlong)]
+
+
+class PnpCfg(C.Structure):
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
+                ("hypotheses", C.c_int), ("sample_size", C.c_int), ("sample_iters", C.c_int),
+                ("refine_iters", C.c_int), ("gate_sq", C.c_float), ("min_depth", C.c_float),
+                ("damping", C.c_float), ("seed", C.c_uint64), ("lanes", C.c_int)]
+
+
+class SynthCfg(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("rows", C.c_int), ("cols", C.c_int),
+                ("keypoint_permille", C.c_int), ("noise_amp", C.c_int)]
+
+
+class TrackCfg(C.Structure):
+    _fields_ = [("match", MatchCfg), ("pnp", PnpCfg), ("top_n", C.c_int), ("max_valid", C.c_int),
+                ("ransac_iters", C.c_int), ("ransac_thr", C.c_float), ("semi_scale", C.c_float)]
+
+
+class PairResult(C.Structure):
+    _fields_ = [("q", C.c_float * 4), ("t", C.c_float * 3), ("pnp_inliers", C.c_float),
+                ("pnp_cost", C.c_float), ("num_matches", C.c_int), ("ransac_inliers", C.c_int),
+                ("best_h", C.c_int), ("status", C.c_int)]
+
+
+def pnp_cfg(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, hypotheses=64, sample_size=8,
+            sample_iters=4, refine_iters=10, gate_sq=9.0, min_depth=0.1, damping=1e-4, seed=0, lanes=1):
+    return PnpCfg(fx, fy, cx, cy, hypotheses, sample_size, sample_iters, refine_iters,
+                  gate_sq, min_depth, damping, seed, lanes)
+
+
+class Oracle:
+    """T2: the parametrised restatement."""
+
+    def __init__(self, fast: bool = False):
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "libmv_oracle_fast.so" if fast else "libmv_oracle.so"))
+        L = self.lib
+        L.orc_softmax.restype = C.c_int
+        L.orc_softmax.argtypes = [C.c_float, _i8p, C.c_int, _i32p, _f32p]
+        L.orc_top_n.restype = C.c_int
+        L.orc_top_n.argtypes = [C.c_float, _i8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _i32p, _i32p, _f32p]
+        L.orc_match.restype = C.c_int
+        L.orc_match.argtypes = [C.POINTER(MatchCfg), _i8p, _i8p, _i32p, _f32p, C.c_int, _i32p, _i32p,
+                                _f32p, _f32p, _i32p, _i32p, _f32p, C.POINTER(MatchStats)]
+        L.orc_svd3.argtypes = [_f32p, _f32p, _f32p, _f32p]
+        L.orc_reproj_error.restype = C.c_float
+        L.orc_reproj_error.argtypes = [_f32p, _f32p, _f32p]
+        L.orc_normalize_points.argtypes = [C.c_int, _f32p, _f32p, _f32p]
+        L.orc_ransac_identity.restype = C.c_int
+        L.orc_ransac_identity.argtypes = [C.c_int, _f32p, _f32p, C.c_int, C.c_float, C.c_int, _f32p, _i32p,
+                                          C.POINTER(C.c_int)]
+        L.orc_recover_pose.argtypes = [_f32p, _f32p, _f32p, _f32p]
+        L.orc_quat_mul.argtypes = [_f32p, _f32p, _f32p]
+        L.orc_apply_transform.argtypes = [_f32p, _f32p, _f32p]
+        L.orc_projection_error.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p]
+        L.orc_matmul.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, _f32p] + [C.c_size_t] * 3 + [C.c_float] * 2 + [C.c_int] * 2
+        L.orc_matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_int] * 2
+        L.orc_pnp_gn.argtypes = [C.POINTER(PnpCfg), C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, _f32p, _f32p, C.c_void_p]
+        L.orc_synth_frame.argtypes = [C.POINTER(SynthCfg), C.c_int, C.c_int, C.c_int, _i8p, _i8p, _f32p]
+        L.orc_track_pair.argtypes = [C.POINTER(TrackCfg), C.c_int, _i8p, _i8p, _f32p, _i8p, _i8p, C.POINTER(PairResult)]
+        L.orc_bench_sequence.restype = C.c_double
+        L.orc_bench_sequence.argtypes = [C.POINTER(TrackCfg), C.POINTER(SynthCfg), _i32p, C.c_int, C.c_int, C.c_int,
+                                         C.POINTER(PairResult)]
+
+    # -- detector
+    def softmax(self, scale, semi):
+        semi = np.ascontiguousarray(semi, np.int8)
+        cells = semi.shape[0]
+        idx = np.zeros(cells, np.int32)
+        pr = np.zeros(cells, np.float32)
+        nv = self.lib.orc_softmax(float(scale), semi, cells, idx, pr)
+        return idx, pr, nv
+
+    def top_n(self, scale, semi, N, max_valid=1000):
+        semi = np.ascontiguousarray(semi, np.int8)
+        pa = np.zeros(N, np.int32); ix = np.zeros(N, np.int32); pr = np.zeros(N, np.float32)
+        n = C.c_int(0)
+        ov = self.lib.orc_top_n(float(scale), semi, semi.shape[0], N, max_valid, C.byref(n), pa, ix, pr)
+        return pa[:n.value].copy(), ix[:n.value].copy(), pr[:n.value].copy(), ov
+
+    # -- matcher
+    def match(self, cfg: MatchCfg, desc0, desc1, max_idx0, probs0, patches1, indices1):
+        M = cfg.max_matches
+        p0 = np.zeros((M, 2), np.float32); p1 = np.zeros((M, 2), np.float32)
+        c0 = np.zeros(M, np.int32); qq = np.zeros(M, np.int32); sc = np.zeros(M, np.float32)
+        st = MatchStats()
+        patches1 = np.ascontiguousarray(patches1, np.int32)
+        indices1 = np.ascontiguousarray(indices1, np.int32)
+        n = self.lib.orc_match(C.byref(cfg), np.ascontiguousarray(desc0, np.int8), np.ascontiguousarray(desc1, np.int8),
+                               np.ascontiguousarray(max_idx0, np.int32), np.ascontiguousarray(probs0, np.float32),
+                               len(patches1), patches1, indices1, p0, p1, c0, qq, sc, C.byref(st))
+        return dict(n=n, pts0=p0[:n].copy(), pts1=p1[:n].copy(), cell0=c0[:n].copy(), query=qq[:n].copy(),
+                    score=sc[:n].copy(), window_cells=st.window_cells, pairs_256=st.pairs_256, pairs_64=st.pairs_64)
+
+    # -- pose
+    def svd3(self, A):
+        A = np.ascontiguousarray(A, np.float32)
+        U = np.zeros((3, 3), np.float32); S = np.zeros((3, 3), np.float32); V = np.zeros((3, 3), np.float32)
+        self.lib.orc_svd3(A, U, S, V)
+        return U, S, V
+
+    def ransac_identity(self, pts1, pts2, iters=10, thr=1.1, cap=1000):
+        pts1 = np.ascontiguousarray(pts1, np.float32); pts2 = np.ascontiguousarray(pts2, np.float32)
+        n = pts1.shape[0]
+        E = np.zeros((3, 3), np.float32); inl = np.zeros(max(cap, 1), np.int32); ni = C.c_int(0)
+        wrote = self.lib.orc_ransac_identity(n, pts1, pts2, iters, thr, cap, E, inl, C.byref(ni))
+        return E, inl[:ni.value].copy(), ni.value, wrote
+
+    def recover_pose(self, E):
+        E = np.ascontiguousarray(E, np.float32)
+        R1 = np.zeros((3, 3), np.float32); R2 = np.zeros((3, 3), np.float32); t = np.zeros(3, np.float32)
+        self.lib.orc_recover_pose(E, R1, R2, t)
+        return R1, R2, t
+
+    def pnp_gn(self, cfg: PnpCfg, corr, n, pair_index=0, init_pose=None, want_hyp=False):
+        corr = np.ascontiguousarray(corr, np.float32)
+        stride = corr.shape[1]
+        pose = np.zeros(7, np.float32); stats = np.zeros(4, np.float32)
+        hyp = np.zeros((cfg.hypotheses, 8), np.float32) if want_hyp else None
+        ip = None if init_pose is None else np.ascontiguousarray(init_pose, np.float32)
+        self.lib.orc_pnp_gn(C.byref(cfg), pair_index, n, stride, corr,
+                            None if ip is None else ip.ctypes.data, pose, stats,
+                            None if hyp is None else hyp.ctypes.data)
+        return pose, stats, hyp
+
+    def synth_frame(self, seed, rows, cols, frame, off_x, off_y, keypoint_permille=140, noise_amp=6):
+        cfg = SynthCfg(seed, rows, cols, keypoint_permille, noise_amp)
+        cells = rows * cols
+        semi = np.zeros((cells, 65), np.int8); desc = np.zeros((cells, 256), np.int8); depth = np.zeros(cells, np.float32)
+        self.lib.orc_synth_frame(C.byref(cfg), frame, off_x, off_y, semi, desc, depth)
+        return semi, desc, depth
+
+    def track_pair(self, cfg: TrackCfg, pair_index, semi0, desc0, depth0, semi1, desc1):
+        out = PairResult()
+        self.lib.orc_track_pair(C.byref(cfg), pair_index, np.ascontiguousarray(semi0), np.ascontiguousarray(desc0),
+                                np.ascontiguousarray(depth0, np.float32), np.ascontiguousarray(semi1),
+                                np.ascontiguousarray(desc1), C.byref(out))
+        return out
+
+    def bench_sequence(self, cfg: TrackCfg, syn: SynthCfg, offsets, first, n, threads):
+        out = (PairResult * n)()
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        secs = self.lib.orc_bench_sequence(C.byref(cfg), C.byref(syn), offsets, first, n, threads, out)
+        return secs, out
+
+
+def have_ref() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libmaveric_ref.so"))
+
+
+class Reference:
+    """T1: the reference's own code (native 24x80 shape, N=100, <=150 matches)."""
+    CELLS = 1920
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libmaveric_ref.so"))
+        L = self.lib
+        L.ref_load_pair.argtypes = [C.c_float, _i8p, C.c_float, _i8p, C.c_float, _i8p, C.c_float, _i8p]
+        L.ref_run_tracking.restype = C.c_int
+        L.ref_run_tracking.argtypes = [_f32p, _f32p, C.POINTER(C.c_int), _i32p, _f32p]
+        L.compute_softmax.argtypes = [C.c_float, _i8p, C.POINTER(C.c_int), _i32p, _f32p]
+        L.compute_top_N.argtypes = [C.c_float, _i8p, C.c_int, C.POINTER(C.c_int), _i32p, _i32p, _f32p]
+        L.ref_ransac_essential_matrix.argtypes = [C.c_int, _f32p, _f32p, _f32p, C.c_int, C.c_float, _f32p, _i32p,
+                                                  C.POINTER(C.c_int)]
+        L.recover_pose_from_essential_matrix.argtypes = [_f32p, _f32p, _f32p, _f32p]
+        L.compute_reprojection_error.restype = C.c_float
+        L.compute_reprojection_error.argtypes = [_f32p, _f32p, _f32p]
+        L.normalize_points.argtypes = [C.c_int, _f32p, _f32p, _f32p]
+        L.svd.argtypes = [C.c_float] * 9 + [C.POINTER(C.c_float)] * 27
+        L.matmul.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, _f32p] + [C.c_size_t] * 3 + [C.c_float] * 2 + [C.c_bool] * 2
+        L.matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_bool] * 2
+
+    def softmax(self, scale, semi):
+        semi = np.ascontiguousarray(semi, np.int8); assert semi.shape == (1920, 65)
+        idx = np.zeros(1920, np.int32); pr = np.zeros(1920, np.float32); nv = C.c_int(0)
+        self.lib.compute_softmax(float(scale), semi, C.byref(nv), idx, pr)
+        return idx, pr, nv.value
+
+    def top_n(self, scale, semi, N):
+        semi = np.ascontiguousarray(semi, np.int8); assert semi.shape == (1920, 65)
+        pa = np.zeros(N, np.int32); ix = np.zeros(N, np.int32); pr = np.zeros(N, np.float32); n = C.c_int(0)
+        self.lib.compute_top_N(float(scale), semi, N, C.byref(n), pa, ix, pr)
+        return pa[:n.value].copy(), ix[:n.value].copy(), pr[:n.value].copy()
+
+    def tracking_main(self, semi_scale0, semi0, desc0, semi_scale1, semi1, desc1):
+        """Runs the reference main() (src/tracking_main.c:68-230) on this pair."""
+        self.lib.ref_load_pair(float(semi_scale0), np.ascontiguousarray(semi0, np.int8), 1.0,
+                               np.ascontiguousarray(desc0, np.int8), float(semi_scale1),
+                               np.ascontiguousarray(semi1, np.int8), 1.0, np.ascontiguousarray(desc1, np.int8))
+        p1 = np.zeros((150, 2), np.float32); p2 = np.zeros((150, 2), np.float32)
+        ni = C.c_int(0); inl = np.zeros(1000, np.int32); E = np.zeros((3, 3), np.float32)
+        n = self.lib.ref_run_tracking(p1, p2, C.byref(ni), inl, E)
+        return dict(n=n, pts0=p1[:n].copy(), pts1=p2[:n].copy(), num_inliers=ni.value,
+                    inliers=inl[:ni.value].copy(), best_E=E)
+
+    def ransac(self, pts1, pts2, K, iters=10, thr=1.1):
+        pts1 = np.ascontiguousarray(pts1, np.float32); pts2 = np.ascontiguousarray(pts2, np.float32)
+        E = np.zeros((3, 3), np.float32); inl = np.zeros(1000, np.int32); ni = C.c_int(-1)
+        self.lib.ref_ransac_essential_matrix(pts1.shape[0], pts1, pts2, np.ascontiguousarray(K, np.float32),
+                                             iters, thr, E, inl, C.byref(ni))
+        return E, inl[:max(ni.value, 0)].copy(), ni.value
+
+    def recover_pose(self, E):
+        E = np.ascontiguousarray(E, np.float32)
+        R1 = np.zeros((3, 3), np.float32); R2 = np.zeros((3, 3), np.float32); t = np.zeros(3, np.float32)
+        self.lib.recover_pose_from_essential_matrix(E, R1, R2, t)
+        return R1, R2, t
+
+    def svd3(self, A):
+        A = np.asarray(A, np.float32)
+        outs = [(C.c_float)() for _ in range(27)]
+        self.lib.svd(*[float(v) for v in A.reshape(-1)], *[C.byref(o) for o in outs])
+        vals = np.array([o.value for o in outs], np.float32)
+        return vals[:9].reshape(3, 3), vals[9:18].reshape(3, 3), vals[18:].reshape(3, 3)
