@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py -- frame-pairs/sec of the tracking hot path (window match + PnP).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by torch.distributed.run, one rank per GPU)
+
+Workload (BASELINE.json configs[3], named in config.workload): a KITTI-00-length synthetic
+sequence -- 4541 frames = 4540 frame pairs of a 47x155-cell grid (376x1241 px), ~1k keypoints
+per frame, radius-4 window search, then per pair the reference's RANSAC-E inlier scan and a
+Gauss-Newton PnP RANSAC with 1024 hypotheses x (4 minimal-sample + 10 refinement) iterations
+over the pair's correspondences.  A step is one pass over all pairs; pairs shard across ranks
+in contiguous blocks (strong scaling) and only the 64-byte per-pair results are all-gathered.
+
+`value`  : device-resident inputs, CUDA-event timed, max over ranks.
+`e2e`    : the same work through mv_track_sequence_host with pinned HOST buffers: per step all
+           frames go host->device (chunked, overlapped with compute) and results come back.
+`roofline`: the dominant kernel (Gauss-Newton PnP; FP32-issue bound) plus
+           `rooflines` for every kernel of the step against its own bound.
+`cpu_baseline`: the CPU port of the same path (oracle/, -O3 -march=native, OpenMP) on a bounded
+           sample of the same pairs on this host.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS, COLS = 47, 155
+N_FRAMES = 4541
+TOP_N, MAX_VALID, MAX_MATCHES = 1000, 8192, 1024
+HYPOTHESES, SAMPLE_ITERS, REFINE_ITERS = 1024, 4, 10
+SEED = 0
+FLOPS_PER_POINT = 125      # FP32 flops of one correspondence in one GN pass
+WORKLOAD = ("KITTI-00-length synthetic sequence: 4541 frames (4540 pairs), 47x155 cells, ~1k keypoints/frame, "
+            "r=4 window match + RANSAC-E + GN-PnP 1024 hyp x (4+10) iters")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured", d.get("sm_max_mhz", 1965.0)
+    return 6650.0, "fallback", 1965.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons streamed during the timed region."""
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index: int, period_ms: int = 50):
+        self.idx = gpu_index
+        self.period_ms = period_ms
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.proc = None
+        self._th = None
+
+    def _reader(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.strip().split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(self.NAMES, f[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self._th = threading.Thread(target=self._reader, daemon=True)
+            self._th.start()
+            time.sleep(0.3)          # first samples land before the timed region starts
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.1)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            if self._th:
+                self._th.join(timeout=2)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def track_cfg_for_oracle(orc, synth):
+    return orc.TrackCfg(orc.MatchCfg(ROWS, COLS, 4, 4, 4, MAX_MATCHES, 0.9, 0.2),
+                        orc.pnp_cfg(hypotheses=HYPOTHESES, sample_iters=SAMPLE_ITERS, refine_iters=REFINE_ITERS,
+                                    seed=SEED, lanes=1),
+                        TOP_N, MAX_VALID, 10, 1.1, float(synth.SEMI_SCALE))
+
+
+def cpu_port_throughput(budget_s: float, n_threads: int | None = None):
+    """Times the CPU port of the same path (oracle/, fast build) on a bounded sample."""
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import synth
+    from oracle import orc
+    o = orc.Oracle(fast=True)
+    cores = n_threads or len(os.sched_getaffinity(0))
+    cfg = track_cfg_for_oracle(orc, synth)
+    syn = orc.SynthCfg(SEED, ROWS, COLS, 140, 6)
+    offs = synth.default_offsets(N_FRAMES, SEED)
+    # calibrate on one pair per thread, then size the sample to the budget
+    t1, _ = o.bench_sequence(cfg, syn, offs[:cores + 1], 0, cores, cores)
+    per_round = max(t1, 1e-3)
+    rounds = int(max(1, min(budget_s / per_round, (N_FRAMES - 1) // cores)))
+    n = min(N_FRAMES - 1, cores * rounds)
+    secs, out = o.bench_sequence(cfg, syn, offs[:n + 1], 0, n, cores)
+    return n / secs, cores, n, secs
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    vals = []
+    n = cores = 0
+    for i in range(args.warmup + args.steps):
+        v, cores, n, secs = cpu_port_throughput(budget_s=max(4.0, 60.0 / max(1, args.steps + args.warmup)))
+        if i >= args.warmup:
+            vals.append((v, secs))
+    value = float(np.mean([v for v, _ in vals]))
+    line = {
+        "impl": "reference", "metric": "frame-pairs/sec (window match + PnP)", "value": value, "unit": "frame-pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int8 match / fp32 PnP", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_pairs_per_step": n},
+        "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+                         "sample": f"first {n} pairs of the same synthetic sequence per step, OpenMP over pairs, "
+                                   "oracle/mv_oracle.c built -O3 -march=native (the reference itself is fixed at 24x80 "
+                                   "cells / N=100 and has no PnP, so its CPU path is timed through the port that is "
+                                   "bit-pinned to it)"},
+        "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=N_FRAMES, help="sequence length (default: KITTI-00, 4541)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--tensor-cores", action="store_true", help="use the tcgen05 matcher")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import synth, tracking
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_frames = args.frames
+    n_pairs = n_frames - 1
+    first, count, per = tracking.shard_pairs(n_pairs, world, rank)
+    tr = tracking.Tracker(local_rank)
+    params = tracking.kitti_track_params(top_n=TOP_N, max_valid=MAX_VALID, max_matches=MAX_MATCHES,
+                                         hypotheses=HYPOTHESES, refine_iters=REFINE_ITERS,
+                                         sample_iters=SAMPLE_ITERS, seed=SEED, first_pair=first,
+                                         use_tensor_cores=args.tensor_cores)
+
+    # ---- inputs: this rank's frames [first, first+count] generated on the device (setup, untimed)
+    offs = synth.default_offsets(n_frames, SEED)
+    my_frames = count + 1
+    semi, desc, depth = tr.synth_frames(SEED, ROWS, COLS, first, offs[first:first + my_frames])
+    scale = torch.full((my_frames,), float(synth.SEMI_SCALE), device=dev)
+    out = torch.empty((count, 64), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    in_bytes = semi.numel() + desc.numel() + depth.numel() * 4
+
+    def step():
+        tr.track_sequence(params, semi, scale, desc, depth, out=out)
+        if world > 1:
+            return tracking.gather_results(out, n_pairs, world)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = tr.ctx.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            res = step()
+        e1.record()
+        barrier()
+    ms = e0.elapsed_time(e1)
+    launches = tr.ctx.launches - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    ms_per_step = ms_max / args.steps
+    value = n_pairs / (ms_per_step * 1e-3)
+
+    # ---- per-kernel device time (CUDA events on the launch stream, separate short pass)
+    tr.ctx.profile(True)
+    for _ in range(2):
+        tr.track_sequence(params, semi, scale, desc, depth, out=out)
+    tr.ctx.sync()
+    prof = {}
+    for tag in ["detect", "topn", "match", "emit", "ransac", "gather", "pnp", "pnp_select"]:
+        prof[tag] = tr.ctx.profile_read(tag)[0]
+    tr.ctx.profile(False)
+
+    resn = tracking.results_to_numpy(out)
+    n_corr = int(resn["num_matches"].sum())
+    hbm_peak, peak_src, sm_max = peaks()
+    cells = ROWS * COLS
+    sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
+    fp32_nominal = sm_count * 128 * 2 * sm_max * 1e6 / 1e12   # TFLOP/s, FMA = 2 flops
+    pnp_flops = (count * HYPOTHESES * SAMPLE_ITERS * 8 + HYPOTHESES * (REFINE_ITERS + 1) * n_corr) * FLOPS_PER_POINT
+    pnp_bytes = 20 * n_corr + 64 * count
+    pnp_ms = prof["pnp"]
+
+    def hbm_entry(name, tag, bytes_):
+        ms_k = prof[tag]
+        ach = bytes_ / (ms_k * 1e-3) / 1e9 if ms_k > 0 else None
+        return {"kernel": name, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                "frac": ach / hbm_peak if ach else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_,
+                "peak_source": peak_src}
+
+    n_q = int(min(TOP_N, 1e9)) * count
+    rooflines = [
+        {"kernel": "pnp_gn_kernel<1> (K3)", "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
+         "peak": fp32_nominal, "unit": "TFLOP/s",
+         "frac": (pnp_flops / (pnp_ms * 1e-3) / 1e12) / fp32_nominal if pnp_ms else None,
+         "ms_per_launch": pnp_ms, "algorithmic_flops": pnp_flops,
+         "peak_source": "nominal: SMs x 128 FMA/clk x 2 x clocks.max.sm from MEASURED_PEAKS.json",
+         "hbm_achieved_gbs": pnp_bytes / (pnp_ms * 1e-3) / 1e9 if pnp_ms else None},
+        hbm_entry("softmax_cells_kernel (K0a)", "detect", my_frames * cells * (65 + 8)),
+        hbm_entry("top_n_kernel (K0b)", "topn", my_frames * (cells * 8 * 2 + TOP_N * 12)),
+        hbm_entry("match_queries_kernel (K1a)", "match",
+                  count * (256 * (TOP_N + int(0.14 * cells) * 2) + 8 * cells + 8 * TOP_N)),
+    ]
+    step_kernel_ms = sum(v for v in prof.values())
+    roofline = dict(rooflines[0])
+    roofline["traffic"] = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        if tj.get("frames") == n_frames and tj.get("n_gpus", 1) == world:
+            roofline["traffic"] = tj.get("pnp_gn_dram_bytes_per_launch")
+            roofline["traffic_source"] = tj.get("source")
+    roofline["share_of_step"] = pnp_ms / step_kernel_ms if step_kernel_ms else None
+
+    # ---- end to end through the host-buffer entry point
+    e2e = None
+    if not args.no_e2e:
+        h_semi = torch.empty(semi.shape, dtype=torch.int8, pin_memory=True)
+        h_desc = torch.empty(desc.shape, dtype=torch.int8, pin_memory=True)
+        h_depth = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True)
+        h_scale = torch.empty(scale.shape, dtype=torch.float32, pin_memory=True)
+        h_semi.copy_(semi); h_desc.copy_(desc); h_depth.copy_(depth); h_scale.copy_(scale)
+        torch.cuda.synchronize()
+        h_out = np.zeros(count, tracking.PAIR_RESULT_DTYPE)
+        up = down = 0
+        for _ in range(2):
+            _, up, down = tr.track_sequence_host(params, h_semi, h_scale, h_desc, h_depth, out=h_out)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, up, down = tr.track_sequence_host(params, h_semi, h_scale, h_desc, h_depth, out=h_out)
+            if world > 1:
+                tracking.gather_results(torch.from_numpy(h_out.view(np.uint8).reshape(-1, 64)).to(dev), n_pairs, world)
+        barrier()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item()) / args.steps
+        same = h_out.tobytes() == resn.tobytes()
+        e2e = {"value": n_pairs / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(up),
+               "d2h_bytes_per_step": int(down), "ms_per_step": e2e_s * 1e3, "results_equal_device_path": bool(same),
+               "api": "mv_track_sequence_host (pinned host buffers, chunked H2D overlapped with compute)"}
+        del h_semi, h_desc, h_depth
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, cores, n, secs = cpu_port_throughput(budget_s=15.0)
+        cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
+               "sample": f"first {n} pairs of the same sequence, {secs:.1f} s, OpenMP over pairs, "
+                         "oracle/mv_oracle.c -O3 -march=native"}
+
+    if rank == 0:
+        line = {
+            "metric": "frame-pairs/sec (window match + PnP)", "value": value, "unit": "frame-pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 match / fp32 PnP", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames": n_frames, "pairs": n_pairs, "grid": [ROWS, COLS],
+                       "top_n": TOP_N, "max_matches": MAX_MATCHES, "hypotheses": HYPOTHESES,
+                       "gn_iters": [SAMPLE_ITERS, REFINE_ITERS], "matcher": "tcgen05" if args.tensor_cores else "dp4a",
+                       "sharding": f"{world} x contiguous pair blocks, all_gather of 64 B/pair",
+                       "cache": f"inputs {in_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
+                       "mean_matches_per_pair": n_corr / max(1, count)},
+            "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "rooflines": rooflines, "kernel_ms": prof, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

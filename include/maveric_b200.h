@@ -159,6 +159,8 @@ typedef struct {
   float damping;            /* relative Levenberg damping added to diag(JtJ) */
   uint64_t seed;            /* counter-based sampling: splitmix64(seed, pair, h, i) */
   int   lanes_per_hypothesis; /* 1: one thread per hypothesis; 32: one warp per hypothesis */
+  int   first_pair;         /* global index of pair 0 of this call: the sampler is keyed on the
+                               global pair index, so results do not depend on chunking/sharding */
 } mv_pnp_params;
 
 void mv_pnp_params_default(mv_pnp_params* p);

@@ -549,7 +549,7 @@ __global__ void pack_results_kernel(int n_pairs, const float* __restrict__ pose,
 
 static mv_status track_sequence_on(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
                                    const float* d_semi_scale, const int8_t* d_desc, const float* d_depth,
-                                   mv_pair_result* d_results, const char* ns) {
+                                   mv_pair_result* d_results, const char* ns, int pair_offset) {
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
   const int N = p->top_n, M = p->match.max_matches;
@@ -591,7 +591,9 @@ static mv_status track_sequence_on(mv_ctx* c, const mv_track_params* p, int n_fr
                                 p->pnp.cx, p->pnp.cy, (const float*)mp, (const int32_t*)mc,
                                 (const int32_t*)mcell, (float*)corr)))
     return st;
-  if ((st = mv_pnp_gn_batch(c, &p->pnp, n_pairs, M, (const float*)corr, (const int32_t*)mc, nullptr,
+  mv_pnp_params pnp = p->pnp;
+  pnp.first_pair += pair_offset;
+  if ((st = mv_pnp_gn_batch(c, &pnp, n_pairs, M, (const float*)corr, (const int32_t*)mc, nullptr,
                             (float*)pose, (float*)stats, nullptr)))
     return st;
   pack_results_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(
@@ -607,7 +609,7 @@ extern "C" mv_status mv_track_sequence(mv_ctx* c, const mv_track_params* p, int 
   if (!c) return MV_ERR_BAD_ARG;
   if (!p || n_frames < 2 || !d_semi || !d_semi_scale || !d_desc || !d_depth || !d_results)
     MV_BAD_ARG(c, "mv_track_sequence");
-  return track_sequence_on(c, p, n_frames, d_semi, d_semi_scale, d_desc, d_depth, d_results, "seq");
+  return track_sequence_on(c, p, n_frames, d_semi, d_semi_scale, d_desc, d_depth, d_results, "seq", 0);
 }
 
 // Host inputs: chunks of frames are staged on the copy stream into one of two device
@@ -626,6 +628,10 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   // chunk size: about 512 MB of frames per buffer, at least 8 pairs
   int chunk_pairs = (int)((512ull << 20) / frame_bytes);
   if (chunk_pairs < 8) chunk_pairs = 8;
+  if (const char* e = getenv("MV_HOST_CHUNK_PAIRS")) {  // test hook: force small chunks
+    const int v = atoi(e);
+    if (v > 0) chunk_pairs = v;
+  }
   if (chunk_pairs > n_pairs) chunk_pairs = n_pairs;
   const int cf = chunk_pairs + 1;
   void *bs[2], *bd[2], *bz[2], *bsc[2], *dres;
@@ -663,7 +669,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     MV_CUDA(c, cudaEventRecord(copied[b], c->copy_stream));
     MV_CUDA(c, cudaStreamWaitEvent(c->stream, copied[b], 0));
     if ((st = track_sequence_on(c, p, nf, (const int8_t*)bs[b], (const float*)bsc[b], (const int8_t*)bd[b],
-                                (const float*)bz[b], (mv_pair_result*)dres + p0, "hseq")))
+                                (const float*)bz[b], (mv_pair_result*)dres + p0, "hseq", p0)))
       return st;
     MV_CUDA(c, cudaEventRecord(consumed[b], c->stream));
   }

@@ -48,7 +48,7 @@ class PnpParams(C.Structure):
     _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float),
                 ("hypotheses", C.c_int), ("sample_size", C.c_int), ("sample_iters", C.c_int),
                 ("refine_iters", C.c_int), ("gate_sq", C.c_float), ("min_depth", C.c_float),
-                ("damping", C.c_float), ("seed", C.c_uint64), ("lanes_per_hypothesis", C.c_int)]
+                ("damping", C.c_float), ("seed", C.c_uint64), ("lanes_per_hypothesis", C.c_int), ("first_pair", C.c_int)]
 
 
 class TrackParams(C.Structure):

@@ -194,7 +194,7 @@ def track(last_frame: Frame | None, current_frame: Frame, x_shift=4, y_shift=4, 
 # --------------------------------------------------------------------------------------
 def track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=1024, radius=4,
                  shift=(4, 4), refine_iters=10, sample_iters=4, ransac_iterations=10, lanes=1, seed=0,
-                 use_tensor_cores=False) -> _lib.TrackParams:
+                 use_tensor_cores=False, first_pair=0) -> _lib.TrackParams:
     p = _lib.TrackParams()
     _lib.load().mv_track_params_default(C.byref(p), rows, cols)
     p.top_n, p.max_valid = top_n, max_valid
@@ -202,7 +202,7 @@ def track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypothe
     p.match.shift_x, p.match.shift_y = shift
     p.match.use_tensor_cores = 1 if use_tensor_cores else 0
     p.pnp.hypotheses, p.pnp.refine_iters, p.pnp.sample_iters = hypotheses, refine_iters, sample_iters
-    p.pnp.lanes_per_hypothesis, p.pnp.seed = lanes, seed
+    p.pnp.lanes_per_hypothesis, p.pnp.seed, p.pnp.first_pair = lanes, seed, first_pair
     p.ransac_iterations = ransac_iterations
     return p
 

@@ -1,0 +1,72 @@
+"""world_size-2 check of the multi-GPU host logic on CPU (gloo): pairs shard in contiguous
+blocks, each rank computes its own block (here with the CPU oracle standing in for the GPU),
+and one all_gather of 64-byte records reproduces the single-rank result on every rank."""
+import os
+import socket
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _records(first, count):
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import tracking
+    rec = np.zeros(count, tracking.PAIR_RESULT_DTYPE)
+    for i in range(count):
+        p = first + i
+        rec[i]["q"] = [1, 0, 0, p]
+        rec[i]["t"] = [p, 2 * p, 3 * p]
+        rec[i]["num_matches"] = 1000 + p
+        rec[i]["best_hypothesis"] = p % 7
+    return rec
+
+
+def _worker(rank, world, port, n_pairs, out_dir):
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import tracking
+    first, count, per = tracking.shard_pairs(n_pairs, world, rank)
+    local = torch.from_numpy(_records(first, count).view(np.uint8).reshape(-1, 64).copy())
+    full = tracking.gather_results(local, n_pairs, world)
+    np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.numpy())
+    dist.destroy_process_group()
+
+
+def test_shard_bounds():
+    sys.path.insert(0, ROOT)
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import tracking
+    for n, w in [(4540, 8), (4540, 1), (5, 8), (17, 4), (0, 2)]:
+        seen = []
+        for r in range(w):
+            first, count, per = tracking.shard_pairs(n, w, r)
+            seen += list(range(first, first + count))
+            assert count <= per
+        assert seen == list(range(n))
+    assert tracking.shard_pairs(4540, 8, 7) == (3976, 564, 568)
+
+
+def test_two_rank_gather_equals_single_rank(tmp_path):
+    n_pairs, world = 37, 2
+    port = _free_port()
+    mp.spawn(_worker, args=(world, port, n_pairs, str(tmp_path)), nprocs=world, join=True)
+    want = _records(0, n_pairs).view(np.uint8).reshape(-1, 64)
+    for r in range(world):
+        got = np.load(os.path.join(str(tmp_path), f"rank{r}.npy"))
+        assert got.shape == want.shape and (got == want).all()
