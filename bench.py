@@ -170,6 +170,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--tensor-cores", action="store_true", help="use the tcgen05 matcher")
+    ap.add_argument("--lanes", type=int, default=1, help="threads cooperating on one PnP hypothesis")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -200,7 +201,7 @@ def main():
     tr = tracking.Tracker(local_rank)
     params = tracking.kitti_track_params(top_n=TOP_N, max_valid=MAX_VALID, max_matches=MAX_MATCHES,
                                          hypotheses=HYPOTHESES, refine_iters=REFINE_ITERS,
-                                         sample_iters=SAMPLE_ITERS, seed=SEED, first_pair=first,
+                                         sample_iters=SAMPLE_ITERS, seed=SEED, first_pair=first, lanes=args.lanes,
                                          use_tensor_cores=args.tensor_cores)
 
     # ---- inputs: this rank's frames [first, first+count] generated on the device (setup, untimed)
@@ -341,7 +342,7 @@ def main():
             "dtype": "int8 match / fp32 PnP", "data": "synthetic",
             "config": {"workload": WORKLOAD, "frames": n_frames, "pairs": n_pairs, "grid": [ROWS, COLS],
                        "top_n": TOP_N, "max_matches": MAX_MATCHES, "hypotheses": HYPOTHESES,
-                       "gn_iters": [SAMPLE_ITERS, REFINE_ITERS], "matcher": "tcgen05" if args.tensor_cores else "dp4a",
+                       "gn_iters": [SAMPLE_ITERS, REFINE_ITERS], "pnp_lanes_per_hypothesis": args.lanes, "matcher": "tcgen05" if args.tensor_cores else "dp4a",
                        "sharding": f"{world} x contiguous pair blocks, all_gather of 64 B/pair",
                        "cache": f"inputs {in_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
                        "mean_matches_per_pair": n_corr / max(1, count)},

@@ -158,7 +158,8 @@ typedef struct {
   float min_depth;          /* cheirality guard on the camera-frame z */
   float damping;            /* relative Levenberg damping added to diag(JtJ) */
   uint64_t seed;            /* counter-based sampling: splitmix64(seed, pair, h, i) */
-  int   lanes_per_hypothesis; /* 1: one thread per hypothesis; 32: one warp per hypothesis */
+  int   lanes_per_hypothesis; /* threads cooperating on one hypothesis: 1 (one thread each) ..
+                               32 (one warp each), a power of two */
   int   first_pair;         /* global index of pair 0 of this call: the sampler is keyed on the
                                global pair index, so results do not depend on chunking/sharding */
 } mv_pnp_params;

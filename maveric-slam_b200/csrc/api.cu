@@ -48,8 +48,13 @@ extern "C" mv_status mv_ctx_create(int device, mv_ctx** out) {
   mv_ctx* c = new mv_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  // the staging stream (copies + detector + row gather) outranks the compute stream so its
+  // short kernels slot in between the CTAs of a long-running PnP launch
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+      cudaStreamCreateWithPriority(&c->gather_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
     delete c;
     return MV_ERR_CUDA;
   }
@@ -62,11 +67,13 @@ extern "C" void mv_ctx_destroy(mv_ctx* c) {
   cudaSetDevice(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
+  cudaStreamSynchronize(c->gather_stream);
   for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
   for (auto& kv : c->scratch) cudaFree(kv.second.first);
   if (c->pinned) cudaFreeHost(c->pinned);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
+  cudaStreamDestroy(c->gather_stream);
   delete c;
 }
 
@@ -547,58 +554,81 @@ __global__ void pack_results_kernel(int n_pairs, const float* __restrict__ pose,
   out[p] = r;
 }
 
-static mv_status track_sequence_on(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
-                                   const float* d_semi_scale, const int8_t* d_desc, const float* d_depth,
-                                   mv_pair_result* d_results, const char* ns, int pair_offset) {
+// Scratch of one in-flight batch of frames ("ns" = arena namespace, so two batches can be
+// in flight in the double-buffered host path).
+struct SeqScratch {
+  int32_t *idx, *qp, *qi, *qc, *ov, *mc, *mcell, *rin;
+  float *prob, *qpr, *mp, *corr, *pose, *stats;
+  uint8_t* flags;
+};
+
+static mv_status seq_scratch(mv_ctx* c, const mv_track_params* p, int n_frames, const char* ns, SeqScratch* o) {
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
   const int N = p->top_n, M = p->match.max_matches;
   std::string s(ns);
-  void *idx, *prob, *qp, *qi, *qpr, *qc, *ov, *mp, *mc, *mcell, *rin, *corr, *pose, *stats;
   mv_status st;
-#define SCR(var, name, bytes) if ((st = mv_scratch(c, (s + name).c_str(), (bytes), &var))) return st
-  SCR(idx, ".idx", sizeof(int32_t) * (size_t)n_frames * cells);
-  SCR(prob, ".prob", sizeof(float) * (size_t)n_frames * cells);
-  SCR(qp, ".qp", sizeof(int32_t) * (size_t)n_frames * N);
-  SCR(qi, ".qi", sizeof(int32_t) * (size_t)n_frames * N);
-  SCR(qpr, ".qpr", sizeof(float) * (size_t)n_frames * N);
-  SCR(qc, ".qc", sizeof(int32_t) * (size_t)n_frames);
-  SCR(ov, ".ov", sizeof(int32_t) * (size_t)n_frames);
-  SCR(mp, ".mp", sizeof(float) * 4 * (size_t)n_pairs * M);
-  SCR(mc, ".mc", sizeof(int32_t) * (size_t)n_pairs);
-  SCR(mcell, ".mcell", sizeof(int32_t) * (size_t)n_pairs * M);
-  SCR(rin, ".rin", sizeof(int32_t) * (size_t)n_pairs);
-  SCR(corr, ".corr", sizeof(float) * 5 * (size_t)n_pairs * M);
-  SCR(pose, ".pose", sizeof(float) * 7 * (size_t)n_pairs);
-  SCR(stats, ".stats", sizeof(float) * 4 * (size_t)n_pairs);
+  void* v;
+#define SCR(field, type, name, bytes) \
+  if ((st = mv_scratch(c, (s + name).c_str(), (bytes), &v))) return st; \
+  o->field = (type*)v
+  SCR(idx, int32_t, ".idx", sizeof(int32_t) * (size_t)n_frames * cells);
+  SCR(prob, float, ".prob", sizeof(float) * (size_t)n_frames * cells);
+  SCR(qp, int32_t, ".qp", sizeof(int32_t) * (size_t)n_frames * N);
+  SCR(qi, int32_t, ".qi", sizeof(int32_t) * (size_t)n_frames * N);
+  SCR(qpr, float, ".qpr", sizeof(float) * (size_t)n_frames * N);
+  SCR(qc, int32_t, ".qc", sizeof(int32_t) * (size_t)n_frames);
+  SCR(ov, int32_t, ".ov", sizeof(int32_t) * (size_t)n_frames);
+  SCR(flags, uint8_t, ".flags", (size_t)n_frames * cells + 64);
+  SCR(mp, float, ".mp", sizeof(float) * 4 * (size_t)n_pairs * M);
+  SCR(mc, int32_t, ".mc", sizeof(int32_t) * (size_t)n_pairs);
+  SCR(mcell, int32_t, ".mcell", sizeof(int32_t) * (size_t)n_pairs * M);
+  SCR(rin, int32_t, ".rin", sizeof(int32_t) * (size_t)n_pairs);
+  SCR(corr, float, ".corr", sizeof(float) * 5 * (size_t)n_pairs * M);
+  SCR(pose, float, ".pose", sizeof(float) * 7 * (size_t)n_pairs);
+  SCR(stats, float, ".stats", sizeof(float) * 4 * (size_t)n_pairs);
 #undef SCR
-  if ((st = mv_softmax_batch(c, n_frames, cells, d_semi, d_semi_scale, (int32_t*)idx, (float*)prob, nullptr)))
-    return st;
-  if ((st = mv_top_n_batch(c, n_frames, cells, N, p->max_valid, (const int32_t*)idx, (const float*)prob,
-                           (int32_t*)qp, (int32_t*)qi, (float*)qpr, (int32_t*)qc, (int32_t*)ov)))
-    return st;
-  if ((st = mv_match_batch(c, &p->match, n_frames, n_pairs, N, nullptr, nullptr, d_desc, (const int32_t*)idx,
-                           (const float*)prob, (const int32_t*)qp, (const int32_t*)qi, (const int32_t*)qc,
-                           (float*)mp, (int32_t*)mc, (int32_t*)mcell, nullptr, nullptr)))
+  return MV_OK;
+}
+
+// Detector half: needs only the logits.
+static mv_status seq_detect(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
+                            const float* d_semi_scale, const SeqScratch& w) {
+  const int cells = p->match.rows * p->match.cols;
+  mv_status st;
+  if ((st = mv_softmax_batch(c, n_frames, cells, d_semi, d_semi_scale, w.idx, w.prob, nullptr))) return st;
+  return mv_top_n_batch(c, n_frames, cells, p->top_n, p->max_valid, w.idx, w.prob, w.qp, w.qi, w.qpr, w.qc, w.ov);
+}
+
+#include <functional>
+static std::function<void(const char*)> g_seq_mark;  // MV_HOST_TRACE debug hook
+
+// Match + pose half: needs descriptors (only rows of candidate / query cells are read) and
+// depth (only at matched frame-0 cells).
+static mv_status seq_match_pose(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_desc,
+                                const float* d_depth, const SeqScratch& w, mv_pair_result* d_results,
+                                int pair_offset) {
+  const int cells = p->match.rows * p->match.cols;
+  const int n_pairs = n_frames - 1;
+  const int N = p->top_n, M = p->match.max_matches;
+  mv_status st;
+  if ((st = mv_match_batch(c, &p->match, n_frames, n_pairs, N, nullptr, nullptr, d_desc, w.idx, w.prob, w.qp, w.qi,
+                           w.qc, w.mp, w.mc, w.mcell, nullptr, nullptr)))
     return st;
   if (p->ransac_iterations > 0) {
-    if ((st = mv_ransac_identity_batch(c, n_pairs, M, (const float*)mp, (const int32_t*)mc,
-                                       p->ransac_iterations, p->ransac_threshold, (int32_t*)rin, nullptr,
-                                       nullptr)))
+    if ((st = mv_ransac_identity_batch(c, n_pairs, M, w.mp, w.mc, p->ransac_iterations, p->ransac_threshold,
+                                       w.rin, nullptr, nullptr)))
       return st;
   }
   if ((st = mv_build_corr_batch(c, n_pairs, cells, p->match.rows, M, nullptr, d_depth, p->pnp.fx, p->pnp.fy,
-                                p->pnp.cx, p->pnp.cy, (const float*)mp, (const int32_t*)mc,
-                                (const int32_t*)mcell, (float*)corr)))
+                                p->pnp.cx, p->pnp.cy, w.mp, w.mc, w.mcell, w.corr)))
     return st;
+  if (g_seq_mark) g_seq_mark("corr_end");
   mv_pnp_params pnp = p->pnp;
   pnp.first_pair += pair_offset;
-  if ((st = mv_pnp_gn_batch(c, &pnp, n_pairs, M, (const float*)corr, (const int32_t*)mc, nullptr,
-                            (float*)pose, (float*)stats, nullptr)))
-    return st;
+  if ((st = mv_pnp_gn_batch(c, &pnp, n_pairs, M, w.corr, w.mc, nullptr, w.pose, w.stats, nullptr))) return st;
   pack_results_kernel<<<(n_pairs + 127) / 128, 128, 0, c->stream>>>(
-      n_pairs, (const float*)pose, (const float*)stats, (const int32_t*)mc,
-      p->ransac_iterations > 0 ? (const int32_t*)rin : nullptr, (const int32_t*)ov, d_results);
+      n_pairs, w.pose, w.stats, w.mc, p->ransac_iterations > 0 ? w.rin : nullptr, w.ov, d_results);
   MV_CHECK_LAUNCH(c);
   return MV_OK;
 }
@@ -609,11 +639,87 @@ extern "C" mv_status mv_track_sequence(mv_ctx* c, const mv_track_params* p, int 
   if (!c) return MV_ERR_BAD_ARG;
   if (!p || n_frames < 2 || !d_semi || !d_semi_scale || !d_desc || !d_depth || !d_results)
     MV_BAD_ARG(c, "mv_track_sequence");
-  return track_sequence_on(c, p, n_frames, d_semi, d_semi_scale, d_desc, d_depth, d_results, "seq", 0);
+  SeqScratch w;
+  mv_status st;
+  if ((st = seq_scratch(c, p, n_frames, "seq", &w))) return st;
+  if ((st = seq_detect(c, p, n_frames, d_semi, d_semi_scale, w))) return st;
+  return seq_match_pose(c, p, n_frames, d_desc, d_depth, w, d_results, 0);
 }
 
-// Host inputs: chunks of frames are staged on the copy stream into one of two device
-// buffers while the previous chunk computes; consecutive chunks share one halo frame.
+// ---- selective staging of descriptors from pinned host memory ------------------------
+// After the detector has run, the matcher will only ever read the descriptor rows of
+//   - frame-0 candidates: argmax != dustbin and !(prob < min_prob0)   (tracking_main.c:142-148)
+//   - frame-1 queries: the cells compute_top_N selected               (tracking_main.c:115-119)
+// and depth only at candidate cells.  So instead of copying every frame's 1.86 MB of
+// descriptors, a kernel pulls just those 256-byte rows straight out of the caller's pinned
+// buffer over PCIe (zero-copy reads) into the same [frame][cell] layout on the device.
+__global__ void mark_needed_rows_kernel(int n_frames, int cells, int top_n, float prob_lt,
+                                        const int32_t* __restrict__ max_idx, const float* __restrict__ prob,
+                                        const int32_t* __restrict__ q_patch, const int32_t* __restrict__ q_count,
+                                        uint8_t* __restrict__ flags) {
+  const int f = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += gridDim.x * blockDim.x) {
+    const size_t g = (size_t)f * cells + i;
+    flags[g] = (max_idx[g] != 64 && !(prob[g] < prob_lt)) ? 1 : 0;
+  }
+}
+__global__ void mark_query_rows_kernel(int cells, int top_n, const int32_t* __restrict__ q_patch,
+                                       const int32_t* __restrict__ q_count, uint8_t* __restrict__ flags) {
+  const int f = blockIdx.y;
+  const int n = min(q_count[f], top_n);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    flags[(size_t)f * cells + q_patch[(size_t)f * top_n + i]] |= 2;
+}
+
+__global__ void __maxnreg__(32)
+gather_rows_kernel(long long total_cells, const uint8_t* __restrict__ flags, const int8_t* __restrict__ h_desc,
+                   const float* __restrict__ h_depth, int8_t* __restrict__ d_desc, float* __restrict__ d_depth,
+                   unsigned long long* __restrict__ rows_moved) {
+  const int lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;  // 16 lanes x 16 B = one 256-byte row
+  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long groups = (total_cells + 31) >> 5;
+  unsigned long long moved = 0;
+  for (long long g = warp; g < groups; g += n_warps) {
+    const long long cell = (g << 5) + lane;
+    const int flag = cell < total_cells ? flags[cell] : 0;
+    if (flag & 1) d_depth[cell] = h_depth[cell];
+    unsigned todo = __ballot_sync(0xffffffffu, flag != 0);
+    moved += __popc(todo);
+    while (todo) {
+      // up to six 256-byte rows in flight per warp: three loads, two rows per load
+      int r[3];
+      int4 v[3];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        int r0 = -1, r1 = -1;
+        if (todo) { r0 = __ffs(todo) - 1; todo &= todo - 1; }
+        if (todo) { r1 = __ffs(todo) - 1; todo &= todo - 1; }
+        r[k] = half ? r1 : r0;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (r[k] >= 0) v[k] = __ldcs(reinterpret_cast<const int4*>(h_desc + ((g << 5) + r[k]) * 256) + l16);
+#pragma unroll
+      for (int k = 0; k < 3; k++)
+        if (r[k] >= 0) reinterpret_cast<int4*>(d_desc + ((g << 5) + r[k]) * 256)[l16] = v[k];
+    }
+  }
+  if (lane == 0 && moved) atomicAdd(rows_moved, moved);
+}
+
+struct StreamSwap {  // run the context's kernels on another stream for a scope
+  mv_ctx* c;
+  cudaStream_t saved;
+  StreamSwap(mv_ctx* ctx, cudaStream_t s) : c(ctx), saved(ctx->stream) { ctx->stream = s; }
+  ~StreamSwap() { c->stream = saved; }
+};
+
+// Host inputs.  Chunks of frames are double-buffered: on the staging stream the logits are
+// copied and the detector runs, then descriptors arrive (selectively when the host buffers
+// are pinned, else as a plain copy); the compute stream matches and solves the previous chunk
+// meanwhile.  Consecutive chunks share one halo frame.
 extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p, int n_frames,
                                             const int8_t* h_semi, const float* h_semi_scale,
                                             const int8_t* h_desc, const float* h_depth,
@@ -624,9 +730,10 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     MV_BAD_ARG(c, "mv_track_sequence_host");
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
-  const size_t frame_bytes = (size_t)cells * (65 + 256 + 4) + 4;
-  // chunk size: about 512 MB of frames per buffer, at least 8 pairs
-  int chunk_pairs = (int)((512ull << 20) / frame_bytes);
+  // chunk = two full waves of the PnP kernel at its capped residency (7 CTAs/SM, see below)
+  const int pnp_ctas_per_pair = (p->pnp.hypotheses + (p->pnp.lanes_per_hypothesis == 1 ? 127 : 15)) /
+                                (p->pnp.lanes_per_hypothesis == 1 ? 128 : 16);
+  int chunk_pairs = 2 * (7 * c->sm_count) / (pnp_ctas_per_pair > 0 ? pnp_ctas_per_pair : 1);
   if (chunk_pairs < 8) chunk_pairs = 8;
   if (const char* e = getenv("MV_HOST_CHUNK_PAIRS")) {  // test hook: force small chunks
     const int v = atoi(e);
@@ -634,50 +741,185 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   }
   if (chunk_pairs > n_pairs) chunk_pairs = n_pairs;
   const int cf = chunk_pairs + 1;
-  void *bs[2], *bd[2], *bz[2], *bsc[2], *dres;
+
+  // zero-copy gather needs device-visible (pinned) descriptor and depth buffers
+  bool gather = true;
+  if (const char* e = getenv("MV_HOST_GATHER")) gather = atoi(e) != 0;
+  const int8_t* hd_desc = nullptr;
+  const float* hd_depth = nullptr;
+  if (gather) {
+    cudaPointerAttributes a1, a2;
+    if (cudaPointerGetAttributes(&a1, h_desc) == cudaSuccess && a1.type == cudaMemoryTypeHost &&
+        cudaPointerGetAttributes(&a2, h_depth) == cudaSuccess && a2.type == cudaMemoryTypeHost &&
+        a1.devicePointer && a2.devicePointer) {
+      hd_desc = (const int8_t*)a1.devicePointer;
+      hd_depth = (const float*)a2.devicePointer;
+    } else {
+      cudaGetLastError();
+      gather = false;  // pageable memory: plain staged copies
+    }
+  }
+
+  constexpr int NB = 3;  // chunks in flight: staging DMA / row gather / compute
+  void *bs[NB], *bd[NB], *bz[NB], *bsc[NB], *dres, *dmoved;
+  SeqScratch w[NB];
   mv_status st;
   const size_t semi_pad = ((size_t)cf * cells * 65 + 255) & ~(size_t)255;
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < NB; b++) {
     const std::string n = "host.buf" + std::to_string(b);
     if ((st = mv_scratch(c, (n + ".semi").c_str(), semi_pad, &bs[b]))) return st;
     if ((st = mv_scratch(c, (n + ".desc").c_str(), (size_t)cf * cells * 256, &bd[b]))) return st;
     if ((st = mv_scratch(c, (n + ".depth").c_str(), sizeof(float) * (size_t)cf * cells, &bz[b]))) return st;
     if ((st = mv_scratch(c, (n + ".scale").c_str(), sizeof(float) * (size_t)cf, &bsc[b]))) return st;
+    if ((st = seq_scratch(c, p, cf, n.c_str(), &w[b]))) return st;
   }
   if ((st = mv_scratch(c, "host.results", sizeof(mv_pair_result) * (size_t)n_pairs, &dres))) return st;
-  cudaEvent_t copied[2], consumed[2];
-  for (int b = 0; b < 2; b++) {
-    MV_CUDA(c, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+  if ((st = mv_scratch(c, "host.moved", 16, &dmoved))) return st;
+  cudaEvent_t ready[NB], consumed[NB], detected[NB], copied[NB];
+  for (int b = 0; b < NB; b++) {
+    MV_CUDA(c, cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
     MV_CUDA(c, cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
+    MV_CUDA(c, cudaEventCreateWithFlags(&detected[b], cudaEventDisableTiming));
+    MV_CUDA(c, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
   }
+  // NB chunks in flight on three engines:
+  //   copy_stream    DMA of a chunk's logits (and descriptors/depth when not gathering)
+  //   stream         in order: detector + row marking of chunk k+1, then match + pose of chunk k
+  //   gather_stream  zero-copy pull of chunk k+1's marked descriptor rows, concurrent with the
+  //                  PnP launch of chunk k.  That launch fills the SMs (7 CTAs x 128 threads x 72
+  //                  registers = all but 1024 registers per SM); the gather kernel is a one-warp,
+  //                  32-register CTA, i.e. exactly the remainder, so it is resident alongside.
+  // whatever the caller queued on the compute stream must be ordered before the staging
+  cudaEvent_t start;
+  MV_CUDA(c, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  MV_CUDA(c, cudaEventRecord(start, c->stream));
+  MV_CUDA(c, cudaStreamWaitEvent(c->copy_stream, start, 0));
+  MV_CUDA(c, cudaStreamWaitEvent(c->gather_stream, start, 0));
+  MV_CUDA(c, cudaMemsetAsync(dmoved, 0, 8, c->gather_stream));
+
+  // MV_HOST_TRACE=1: timestamp every stage of every chunk (debug aid, prints to stderr)
+  const bool trace = getenv("MV_HOST_TRACE") != nullptr;
+  std::vector<std::pair<std::string, cudaEvent_t>> marks;
+  auto mark = [&](const char* what, int chunk, cudaStream_t s) {
+    if (!trace) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    marks.push_back({std::string(what) + "#" + std::to_string(chunk), e});
+  };
+  mark("start", 0, c->stream);
+
   unsigned long long up = 0;
-  int b = 0;
-  for (int p0 = 0; p0 < n_pairs; p0 += chunk_pairs, b ^= 1) {
-    const int np = (n_pairs - p0) < chunk_pairs ? (n_pairs - p0) : chunk_pairs;
-    const int nf = np + 1;
-    // the copy engine may refill buffer b only after the compute that read it is done
-    MV_CUDA(c, cudaStreamWaitEvent(c->copy_stream, consumed[b], 0));
+  const int n_chunks = (n_pairs + chunk_pairs - 1) / chunk_pairs;
+  auto chunk_first = [&](int k) { return k * chunk_pairs; };
+  auto chunk_frames = [&](int k) {
+    const int p0 = k * chunk_pairs;
+    return ((n_pairs - p0) < chunk_pairs ? (n_pairs - p0) : chunk_pairs) + 1;
+  };
+
+  auto stage_dma = [&](int k) -> mv_status {
+    const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
+    cudaStream_t cs = c->copy_stream;
+    // buffer set b may be refilled only after the compute that read it is done
+    MV_CUDA(c, cudaStreamWaitEvent(cs, consumed[b], 0));
+    mark("dma_beg", k, cs);
     MV_CUDA(c, cudaMemcpyAsync(bs[b], h_semi + (size_t)p0 * cells * 65, (size_t)nf * cells * 65,
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    MV_CUDA(c, cudaMemcpyAsync(bd[b], h_desc + (size_t)p0 * cells * 256, (size_t)nf * cells * 256,
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    MV_CUDA(c, cudaMemcpyAsync(bz[b], h_depth + (size_t)p0 * cells, sizeof(float) * (size_t)nf * cells,
-                               cudaMemcpyHostToDevice, c->copy_stream));
-    MV_CUDA(c, cudaMemcpyAsync(bsc[b], h_semi_scale + p0, sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice,
-                               c->copy_stream));
-    up += (unsigned long long)nf * ((size_t)cells * (65 + 256 + 4) + 4);
-    MV_CUDA(c, cudaEventRecord(copied[b], c->copy_stream));
+                               cudaMemcpyHostToDevice, cs));
+    MV_CUDA(c, cudaMemcpyAsync(bsc[b], h_semi_scale + p0, sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice, cs));
+    up += (unsigned long long)nf * ((size_t)cells * 65 + 4);
+    if (!gather) {
+      MV_CUDA(c, cudaMemcpyAsync(bd[b], h_desc + (size_t)p0 * cells * 256, (size_t)nf * cells * 256,
+                                 cudaMemcpyHostToDevice, cs));
+      MV_CUDA(c, cudaMemcpyAsync(bz[b], h_depth + (size_t)p0 * cells, sizeof(float) * (size_t)nf * cells,
+                                 cudaMemcpyHostToDevice, cs));
+      up += (unsigned long long)nf * (size_t)cells * (256 + 4);
+    }
+    MV_CUDA(c, cudaEventRecord(copied[b], cs));
+    mark("dma_end", k, cs);
+    return MV_OK;
+  };
+  auto stage_detect = [&](int k) -> mv_status {
+    const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
+    mv_status s2;
     MV_CUDA(c, cudaStreamWaitEvent(c->stream, copied[b], 0));
-    if ((st = track_sequence_on(c, p, nf, (const int8_t*)bs[b], (const float*)bsc[b], (const int8_t*)bd[b],
-                                (const float*)bz[b], (mv_pair_result*)dres + p0, "hseq", p0)))
-      return st;
+    if ((s2 = seq_detect(c, p, nf, (const int8_t*)bs[b], (const float*)bsc[b], w[b]))) return s2;
+    if (gather) {
+      dim3 g1((cells + 255) / 256, nf), g2((p->top_n + 255) / 256, nf);
+      mark_needed_rows_kernel<<<g1, 256, 0, c->stream>>>(nf, cells, p->top_n, mv_round_up(p->match.min_prob0),
+                                                         w[b].idx, w[b].prob, w[b].qp, w[b].qc, w[b].flags);
+      MV_CHECK_LAUNCH(c);
+      mark_query_rows_kernel<<<g2, 256, 0, c->stream>>>(cells, p->top_n, w[b].qp, w[b].qc, w[b].flags);
+      MV_CHECK_LAUNCH(c);
+    }
+    MV_CUDA(c, cudaEventRecord(detected[b], c->stream));
+    mark("det_end", k, c->stream);
+    if (gather) {
+      cudaStream_t gs = c->gather_stream;
+      MV_CUDA(c, cudaStreamWaitEvent(gs, detected[b], 0));
+      mark("gat_beg", k, gs);
+      // An SM's L1/shared split is per-SM state: a kernel that asks for no shared memory
+      // configures "all L1", and the PnP CTAs (7 x 21 KB shared) then cannot join that SM until
+      // it drains.  Ask for the max-shared carveout so both kernels agree on the split.
+      static bool carveout_set = false;
+      if (!carveout_set) {
+        cudaFuncSetAttribute(gather_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        carveout_set = true;
+      }
+      gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>(
+          (long long)nf * cells, w[b].flags, hd_desc + (size_t)p0 * cells * 256, hd_depth + (size_t)p0 * cells,
+          (int8_t*)bd[b], (float*)bz[b], (unsigned long long*)dmoved);
+      MV_CHECK_LAUNCH(c);
+      MV_CUDA(c, cudaEventRecord(ready[b], gs));
+      mark("gat_end", k, gs);
+    } else {
+      MV_CUDA(c, cudaEventRecord(ready[b], c->stream));
+    }
+    return MV_OK;
+  };
+  auto stage_compute = [&](int k) -> mv_status {
+    const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
+    mv_status s2;
+    MV_CUDA(c, cudaStreamWaitEvent(c->stream, ready[b], 0));
+    mark("cmp_beg", k, c->stream);
+    if (trace) g_seq_mark = [&, k](const char* what) { mark(what, k, c->stream); };
+    if ((s2 = seq_match_pose(c, p, nf, (const int8_t*)bd[b], (const float*)bz[b], w[b],
+                             (mv_pair_result*)dres + p0, p0)))
+      return s2;
+    g_seq_mark = nullptr;
     MV_CUDA(c, cudaEventRecord(consumed[b], c->stream));
+    mark("cmp_end", k, c->stream);
+    return MV_OK;
+  };
+
+  if ((st = stage_dma(0))) return st;
+  if (n_chunks > 1 && (st = stage_dma(1))) return st;
+  if ((st = stage_detect(0))) return st;
+  for (int k = 0; k < n_chunks; k++) {
+    if (k + 2 < n_chunks && (st = stage_dma(k + 2))) return st;
+    if (k + 1 < n_chunks && (st = stage_detect(k + 1))) return st;
+    if ((st = stage_compute(k))) return st;
   }
+  unsigned long long moved = 0;
   MV_CUDA(c, cudaMemcpyAsync(h_results, dres, sizeof(mv_pair_result) * (size_t)n_pairs, cudaMemcpyDeviceToHost,
                              c->stream));
   MV_CUDA(c, cudaStreamSynchronize(c->stream));
   MV_CUDA(c, cudaStreamSynchronize(c->copy_stream));
-  for (int i = 0; i < 2; i++) { cudaEventDestroy(copied[i]); cudaEventDestroy(consumed[i]); }
+  MV_CUDA(c, cudaMemcpyAsync(&moved, dmoved, 8, cudaMemcpyDeviceToHost, c->gather_stream));
+  MV_CUDA(c, cudaStreamSynchronize(c->gather_stream));
+  for (int i = 0; i < NB; i++) {
+    cudaEventDestroy(ready[i]); cudaEventDestroy(consumed[i]); cudaEventDestroy(detected[i]); cudaEventDestroy(copied[i]);
+  }
+  cudaEventDestroy(start);
+  if (trace) {
+    for (auto& m : marks) {
+      float ms = 0.f;
+      cudaEventElapsedTime(&ms, marks[0].second, m.second);
+      fprintf(stderr, "[mv trace] %-12s %9.3f ms\n", m.first.c_str(), ms);
+    }
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+  if (gather) up += moved * 260ull;  // 256 B descriptor row + 4 B depth per staged cell
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = sizeof(mv_pair_result) * (unsigned long long)n_pairs;
   return MV_OK;

@@ -12,8 +12,6 @@
 
 namespace {
 
-constexpr int kTileCells = 256;                 // cells per CTA
-constexpr int kTileBytes = kTileCells * 65;     // 16640, a multiple of 16
 constexpr int kTaylorTerms = 5;                 // top_N.c:7
 
 // top_N.c:59-63
@@ -39,11 +37,13 @@ __device__ __forceinline__ float taylor_exp(const float c[kTaylorTerms], int x) 
 // shared memory with 16-byte loads, then one thread walks one cell word by word;
 // words without a non-negative byte (the common case, ~97 % of logits are negative)
 // are skipped with one mask test.
+template <int kTileCells>  // kTileCells * 65 must be a multiple of 16
 __global__ void __launch_bounds__(kTileCells)
 softmax_cells_kernel(const int8_t* __restrict__ semi, const float* __restrict__ scale,
                      long long total_cells, int cells_per_frame, int vec_ok,
                      int32_t* __restrict__ max_idx, float* __restrict__ prob,
                      int32_t* __restrict__ num_valid) {
+  constexpr int kTileBytes = kTileCells * 65;
   __shared__ __align__(16) uint8_t tile[kTileBytes + 16];
   const long long cell0 = (long long)blockIdx.x * kTileCells;
   const long long remaining = total_cells - cell0;
@@ -112,55 +112,23 @@ softmax_cells_kernel(const int8_t* __restrict__ semi, const float* __restrict__ 
 }
 
 // ---- K0b -----------------------------------------------------------------
-constexpr int kTopNThreads = 512;
-
-__device__ __forceinline__ int block_exclusive_scan(int v, int* total, int* warp_sums) {
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int inc = v;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    int n = __shfl_up_sync(0xffffffffu, inc, o);
-    if (lane >= o) inc += n;
-  }
-  if (lane == 31) warp_sums[wid] = inc;
-  __syncthreads();
-  if (wid == 0) {
-    int s = lane < (kTopNThreads / 32) ? warp_sums[lane] : 0;
-    int si = s;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      int n = __shfl_up_sync(0xffffffffu, si, o);
-      if (lane >= o) si += n;
-    }
-    if (lane < (kTopNThreads / 32)) warp_sums[lane] = si - s;  // exclusive warp offsets
-    if (lane == 31) *total = si;
-  }
-  __syncthreads();
-  const int out = warp_sums[wid] + inc - v;
-  __syncthreads();
-  return out;
-}
-
-// One CTA per frame.  Pass 1: count the valid cells and their prob range.  Pass 2:
-// ordered compaction of the first top_n cells whose prob clears the interpolated cut.
-__global__ void __launch_bounds__(kTopNThreads)
+// One warp per frame (a one-warp CTA, low profile like the 32-cell softmax): pass 1 counts
+// the valid cells and their prob range, pass 2 is a ballot-ordered compaction of the first
+// top_n cells whose prob clears the interpolated cut.  Selection is sparse (<= top_n of
+// thousands of cells), so a frame is two coalesced sweeps of its 8 B/cell detector output.
+__global__ void __launch_bounds__(32)
 top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob, int cells,
              int top_n, int max_valid, float valid_gt /* round_down(0.01) */,
              int32_t* __restrict__ q_patch, int32_t* __restrict__ q_idx, float* __restrict__ q_prob,
              int32_t* __restrict__ q_count, int32_t* __restrict__ overflow) {
-  __shared__ int s_warp[kTopNThreads / 32];
-  __shared__ float s_hi[kTopNThreads / 32], s_lo[kTopNThreads / 32];
-  __shared__ int s_total, s_nv, s_base;
-  __shared__ float s_cut;
-
   const int f = blockIdx.x;
+  const int lane = threadIdx.x;
   const int32_t* mi = max_idx + (size_t)f * cells;
   const float* pr = prob + (size_t)f * cells;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 
   int nv = 0;
   float hi = 0.0f, lo = FLT_MAX;  // top_N.c:69
-  for (int p = threadIdx.x; p < cells; p += kTopNThreads) {
+  for (int p = lane; p < cells; p += 32) {
     const float v = pr[p];
     if (mi[p] != 64 && v > valid_gt) {  // top_N.c:77
       nv++;
@@ -174,62 +142,44 @@ top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
   }
-  if (lane == 0) { s_warp[wid] = nv; s_hi[wid] = hi; s_lo[wid] = lo; }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    int tn = 0;
-    float th = 0.0f, tl = FLT_MAX;
-    for (int w = 0; w < kTopNThreads / 32; w++) {
-      tn += s_warp[w];
-      th = fmaxf(th, s_hi[w]);
-      tl = fminf(tl, s_lo[w]);
-    }
-    s_nv = tn;
-    float cut = -FLT_MAX;  // nv <= N: take every valid cell (top_N.c:98-106)
-    if (tn > top_n) {      // top_N.c:108-109
-      const float split = __fdiv_rn((float)top_n, (float)tn);
-      cut = __fadd_rn(__fmul_rn(th, split), __fmul_rn(tl, __fsub_rn(1.0f, split)));
-    }
-    s_cut = cut;
-    s_base = 0;
-  }
-  __syncthreads();
-  const int total_valid = s_nv;
-  if (total_valid >= max_valid) {  // top_N.c:91-94: the reference exits here
-    if (threadIdx.x == 0) {
+  if (nv >= max_valid) {  // top_N.c:91-94: the reference exits here
+    if (lane == 0) {
       q_count[f] = 0;
       if (overflow) overflow[f] = 1;
     }
     return;
   }
-  const float cut = s_cut;
+  float cut = -FLT_MAX;  // nv <= N: take every valid cell (top_N.c:98-106)
+  if (nv > top_n) {      // top_N.c:108-109
+    const float split = __fdiv_rn((float)top_n, (float)nv);
+    cut = __fadd_rn(__fmul_rn(hi, split), __fmul_rn(lo, __fsub_rn(1.0f, split)));
+  }
 
   int32_t* op = q_patch + (size_t)f * top_n;
   int32_t* oi = q_idx + (size_t)f * top_n;
   float* opr = q_prob + (size_t)f * top_n;
-  for (int p0 = 0; p0 < cells; p0 += kTopNThreads) {
-    const int p = p0 + threadIdx.x;
-    int take = 0, ch = 64;
+  int taken = 0;
+  for (int p0 = 0; p0 < cells && taken < top_n; p0 += 32) {  // top_N.c:116-133
+    const int p = p0 + lane;
+    int ch = 64;
     float v = 0.0f;
+    bool take = false;
     if (p < cells) {
       ch = mi[p];
       v = pr[p];
-      take = (ch != 64 && v > valid_gt && v >= cut) ? 1 : 0;  // top_N.c:121
+      take = ch != 64 && v > valid_gt && v >= cut;  // top_N.c:121
     }
-    const int base = s_base;
-    const int pos = base + block_exclusive_scan(take, &s_total, s_warp);
+    const unsigned votes = __ballot_sync(0xffffffffu, take);
+    const int pos = taken + __popc(votes & ((1u << lane) - 1));
     if (take && pos < top_n) {
       op[pos] = p;
       oi[pos] = ch;
       opr[pos] = v;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_base = base + s_total;
-    __syncthreads();
-    if (s_base >= top_n) break;  // top_N.c:128-130
+    taken += __popc(votes);
   }
-  if (threadIdx.x == 0) {
-    q_count[f] = s_base < top_n ? s_base : top_n;
+  if (lane == 0) {
+    q_count[f] = taken < top_n ? taken : top_n;
     if (overflow) overflow[f] = 0;
   }
 }
@@ -243,12 +193,11 @@ extern "C" mv_status mv_softmax_batch(mv_ctx* ctx, int n_frames, int cells, cons
   if (n_frames <= 0 || cells <= 0 || !d_semi || !d_semi_scale || !d_max_idx || !d_prob)
     MV_BAD_ARG(ctx, "mv_softmax_batch");
   const long long total = (long long)n_frames * cells;
-  const int grid = (int)((total + kTileCells - 1) / kTileCells);
   const int vec_ok = (reinterpret_cast<uintptr_t>(d_semi) & 15) == 0;
   if (d_num_valid) MV_CUDA(ctx, cudaMemsetAsync(d_num_valid, 0, sizeof(int32_t) * n_frames, ctx->stream));
   mv_prof_scope ps(ctx, "detect");
-  softmax_cells_kernel<<<grid, kTileCells, 0, ctx->stream>>>(d_semi, d_semi_scale, total, cells, vec_ok,
-                                                             d_max_idx, d_prob, d_num_valid);
+  softmax_cells_kernel<256><<<(unsigned)((total + 255) / 256), 256, 0, ctx->stream>>>(
+      d_semi, d_semi_scale, total, cells, vec_ok, d_max_idx, d_prob, d_num_valid);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }
@@ -262,7 +211,7 @@ extern "C" mv_status mv_top_n_batch(mv_ctx* ctx, int n_frames, int cells, int to
       !d_q_patch || !d_q_idx || !d_q_prob || !d_q_count)
     MV_BAD_ARG(ctx, "mv_top_n_batch");
   mv_prof_scope ps(ctx, "topn");
-  top_n_kernel<<<n_frames, kTopNThreads, 0, ctx->stream>>>(d_max_idx, d_prob, cells, top_n, max_valid,
+  top_n_kernel<<<n_frames, 32, 0, ctx->stream>>>(d_max_idx, d_prob, cells, top_n, max_valid,
                                                            mv_round_down(0.01), d_q_patch, d_q_idx,
                                                            d_q_prob, d_q_count, d_overflow);
   MV_CHECK_LAUNCH(ctx);

@@ -28,7 +28,9 @@ struct mv_ctx {
   int sm_count = 148;
   cudaStream_t stream = nullptr;      // compute stream (owned unless set_stream)
   bool own_stream = true;
-  cudaStream_t copy_stream = nullptr; // H2D staging for the host-buffer sequence call
+  cudaStream_t copy_stream = nullptr; // host-buffer sequence call: logits DMA + detector (high priority)
+  cudaStream_t gather_stream = nullptr; // host-buffer sequence call: selective descriptor staging
+  int pnp_max_ctas_per_sm = 0;        // >0: cap K3 residency so staging kernels can co-reside
   char err[512] = {0};
   unsigned long long launches = 0;
   bool profile = false;

@@ -623,17 +623,17 @@ static void ne_add_point(ne_acc* acc, const float R[9], const float t[3], const 
   acc->cnt += w;
 }
 
-/* xor-butterfly over 32 lane partials, the order a warp shuffle reduction uses */
-static void ne_butterfly(ne_acc lane[32]) {
-  for (int off = 16; off >= 1; off >>= 1) {
+/* xor-butterfly over L lane partials, the order a shuffle reduction uses */
+static void ne_butterfly(ne_acc lane[32], int L) {
+  for (int off = L / 2; off >= 1; off >>= 1) {
     ne_acc nxt[32];
-    for (int l = 0; l < 32; l++) {
+    for (int l = 0; l < L; l++) {
       for (int k = 0; k < 21; k++) nxt[l].H[k] = lane[l].H[k] + lane[l ^ off].H[k];
       for (int k = 0; k < 6; k++) nxt[l].g[k] = lane[l].g[k] + lane[l ^ off].g[k];
       nxt[l].cost = lane[l].cost + lane[l ^ off].cost;
       nxt[l].cnt = lane[l].cnt + lane[l ^ off].cnt;
     }
-    memcpy(lane, nxt, sizeof(nxt));
+    memcpy(lane, nxt, sizeof(ne_acc) * (size_t)L);
   }
 }
 
@@ -707,14 +707,15 @@ static void ne_all_points(ne_acc* out, const orc_pnp_cfg* c, const float R[9], c
                           int n, int stride, const float* corr, int gated) {
   const float *PX = corr, *PY = corr + stride, *PZ = corr + 2 * stride, *PU = corr + 3 * stride,
               *PV = corr + 4 * stride;
-  if (c->lanes == 32) {
+  if (c->lanes > 1) {
+    const int L = c->lanes;
     ne_acc lane[32];
-    for (int l = 0; l < 32; l++) {
+    for (int l = 0; l < L; l++) {
       ne_zero(&lane[l]);
-      for (int j = l; j < n; j += 32)
+      for (int j = l; j < n; j += L)
         ne_add_point(&lane[l], R, t, c, PX[j], PY[j], PZ[j], PU[j], PV[j], gated);
     }
-    ne_butterfly(lane);
+    ne_butterfly(lane, L);
     *out = lane[0];
   } else {
     ne_zero(out);
@@ -726,16 +727,17 @@ static void ne_sample_points(ne_acc* out, const orc_pnp_cfg* c, const float R[9]
                              int stride, const float* corr, const int* sample) {
   const float *PX = corr, *PY = corr + stride, *PZ = corr + 2 * stride, *PU = corr + 3 * stride,
               *PV = corr + 4 * stride;
-  if (c->lanes == 32) {
+  if (c->lanes > 1) {
+    const int L = c->lanes;
     ne_acc lane[32];
-    for (int l = 0; l < 32; l++) {
+    for (int l = 0; l < L; l++) {
       ne_zero(&lane[l]);
-      for (int i = l; i < c->sample_size; i += 32) {
+      for (int i = l; i < c->sample_size; i += L) {
         int j = sample[i];
         ne_add_point(&lane[l], R, t, c, PX[j], PY[j], PZ[j], PU[j], PV[j], 0);
       }
     }
-    ne_butterfly(lane);
+    ne_butterfly(lane, L);
     *out = lane[0];
   } else {
     ne_zero(out);

@@ -74,7 +74,7 @@ typedef struct {
   int hypotheses, sample_size, sample_iters, refine_iters;
   float gate_sq, min_depth, damping;
   uint64_t seed;
-  int lanes;   /* 1: sequential sums; 32: lane-strided partial sums + xor butterfly */
+  int lanes;   /* 1: sequential sums; 2..32 (power of two): lane-strided partials + xor butterfly */
 } orc_pnp_cfg;
 /* corr: SoA planes X,Y,Z,u,v each `stride` floats.  out_pose[7], out_stats[4] =
  * {inliers,cost,best_h,valid}; hyp_pose (nullable) [H][8]. */

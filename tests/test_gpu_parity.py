@@ -214,7 +214,7 @@ def _pnp_params(tk, H, lanes, seed=0, refine=10):
     return p
 
 
-@pytest.mark.parametrize("lanes", [1, 32])
+@pytest.mark.parametrize("lanes", [1, 4, 8, 32])
 @pytest.mark.parametrize("n,stride", [(1000, 1024), (37, 64), (1500, 1536), (8, 8)])
 def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, n, stride):
     import torch
