@@ -1,8 +1,482 @@
-// placeholder, replaced below
+// match_tc.cu -- windowed int8 descriptor search on the 5th-generation tensor cores
+// (reference: src/tracking_main.c:18-43,103-194; same results as match.cu, bit for bit).
+//
+// The reference evaluates a 64-dimension dot product for every candidate of a query but the
+// first one (squared_dist, tracking_main.c:33-41), so the bulk of the search is an int8 GEMM
+//     D[query][cell] = sum_{k<64} desc1[query][k] * desc0[cell][k]
+// over the cells of the query's search window.  A work item is a tile of 128 consecutive
+// queries of one frame pair; its candidates are the full cell columns spanned by the union of
+// the queries' windows, "the window as a TMA box" (SURVEY §7):
+//
+//   warp 0      TMA producer: one 4-D box [64 B][rows][Cx columns][1 frame] of frame 0's
+//               descriptor tensor per chunk, SWIZZLE_64B, into a 6-deep shared-memory ring
+//   warp 1      MMA issuer: per chunk two tcgen05.mma.kind::i8 (M=128, N=Cx*rows<=256, K=32)
+//               into one of two 256-column TMEM accumulator stages
+//   warps 2-3   query gather: the first 64 bytes of the tile's 128 query descriptors into the
+//               A operand (same swizzle), and the validity bits of the tile's cell range
+//   warps 4-11  epilogue, thread <-> query row (TMEM lane), two threads per row splitting the
+//               32-column blocks: tcgen05.ld, window/validity mask, and the reference's exact
+//               score only for the rare element that can still win (see "filter" below)
+//
+// The distance matrix never leaves TMEM.  The one 256-dimension evaluation per query
+// (squared_dist's first call, tracking_main.c:21-32, sticky while the candidate norm is 0) is
+// done by the epilogue thread with dp4a before the tile's chunks arrive.
+//
+// Filter.  For the non-leading candidates of a query the score (tracking_main.c:154) is
+//     s = float(int32(dot*dot)) / float(int32(norm_F * norm_q64))
+// with a denominator that is constant per query.  int->float and IEEE division are monotone,
+// so s is non-decreasing in key = n (denominator >= 0) or key = ~n (denominator < 0), n the
+// wrapped int32 square.  A candidate whose key does not exceed the largest key seen so far can
+// neither pass the threshold nor beat the current best (strict '>' at :155-156), so the exact
+// float path runs only on strict prefix maxima of the key, which start above a conservative
+// bound derived from the acceptance threshold.  Ties keep the smaller cell index = the
+// earlier candidate in the reference's x-outer / y-inner scan.
 #include "mv_common.cuh"
-mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params*, int, int, int, const int32_t*, const int32_t*,
-                             const int8_t*, const int32_t*, const float*, const int32_t*, const int32_t*,
-                             int32_t*, float*) {
-  snprintf(ctx->err, sizeof(ctx->err), "tensor-core matcher not built");
-  return MV_ERR_BAD_ARG;
+#include "sm100_ptx.cuh"
+
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileQ = 128;
+constexpr int kBStages = 6;
+constexpr int kBStageBytes = 256 * 64;
+constexpr int kAStages = 2;
+constexpr int kAStageBytes = kTileQ * 64;
+constexpr int kAccStages = 2;
+constexpr int kAccCols = 256;
+constexpr int kGatherThreads = 64;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (4 + kEpiWarps);
+constexpr int kVPadWords = 12;   // zero words after a frame's validity bits (chunk overrun + funnel)
+
+struct TcGeom {
+  int rows, cols, cells, shift_x, shift_y, radius, top_n;
+  int cx;             // cell columns per chunk
+  int n_chunk;        // UMMA N: cx*rows rounded up to 16
+  int vwords;         // validity words per frame (incl. padding)
+  int tiles_per_pair, n_items;
+  float accept_gt;    // (double)s > thr^2  <=>  s > accept_gt
+  float prob_lt;      // (double)p < min    <=>  p < prob_lt
+};
+
+// bit c of frame f's word array: cell c is a candidate (tracking_main.c:142,146)
+__global__ void valid_bits_kernel(int cells, int vwords, float prob_lt, const int32_t* __restrict__ max_idx,
+                                  const float* __restrict__ prob, uint32_t* __restrict__ vbits) {
+  const int f = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  bool v = false;
+  if (c < cells) v = (max_idx[(size_t)f * cells + c] != 64) && !(prob[(size_t)f * cells + c] < prob_lt);
+  const unsigned w = __ballot_sync(0xffffffffu, v);
+  if ((threadIdx.x & 31) == 0 && (c >> 5) < vwords) vbits[(size_t)f * vwords + (c >> 5)] = w;
+}
+
+struct TileSpan {
+  int f0, f1, q0, n_rows;   // n_rows == 0: nothing to do
+  int X0, n_chunks;         // first candidate column, chunks of cx columns
+};
+
+// Warp-collective: the tile's query count and the cell columns its windows span.
+__device__ __forceinline__ TileSpan tile_span(const TcGeom& g, int item, const int32_t* __restrict__ f0_of,
+                                              const int32_t* __restrict__ f1_of,
+                                              const int32_t* __restrict__ q_patch,
+                                              const int32_t* __restrict__ q_count) {
+  TileSpan t;
+  const int pair = item / g.tiles_per_pair;
+  t.q0 = (item - pair * g.tiles_per_pair) * kTileQ;
+  t.f0 = f0_of ? f0_of[pair] : pair;
+  t.f1 = f1_of ? f1_of[pair] : pair + 1;
+  const int nq = min(q_count[t.f1], g.top_n);
+  t.n_rows = max(0, min(kTileQ, nq - t.q0));
+  int xmin = 0x7fffffff, xmax = -1;
+  for (int r = threadIdx.x & 31; r < t.n_rows; r += 32) {
+    const int x = q_patch[(size_t)t.f1 * g.top_n + t.q0 + r] / g.rows;
+    xmin = min(xmin, x);
+    xmax = max(xmax, x);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    xmin = min(xmin, __shfl_xor_sync(0xffffffffu, xmin, o));
+    xmax = max(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
+  }
+  t.X0 = max(xmin + g.shift_x - g.radius, 0);
+  const int X1 = min(xmax + g.shift_x + g.radius, g.cols - 1);
+  t.n_chunks = (t.n_rows > 0 && X1 >= t.X0) ? (X1 - t.X0 + g.cx) / g.cx : 0;
+  return t;
+}
+
+__device__ __forceinline__ int first_set_in_range(const uint32_t* sv, int base_bit, int lo, int hi) {
+  int p = lo - base_bit;
+  const int e = hi - base_bit;
+  while (p <= e) {
+    const uint32_t w = sv[p >> 5] >> (p & 31);
+    if (w) {
+      const int q = p + __ffs(w) - 1;
+      return q <= e ? q + base_bit : -1;
+    }
+    p = (p | 31) + 1;
+  }
+  return -1;
+}
+
+// tracking_main.c:154 with defined (two's complement) wrap
+__device__ __forceinline__ float wrapped_cos2(int dot, int n_cand, int n_query) {
+  const int num = (int)((unsigned)dot * (unsigned)dot);
+  const int den = (int)((unsigned)n_cand * (unsigned)n_query);
+  return __fdiv_rn(__int2float_rn(num), __int2float_rn(den));
+}
+
+__device__ __forceinline__ int dp4a4(const int4& a, const int4& b, int acc) {
+  acc = __dp4a(a.x, b.x, acc);
+  acc = __dp4a(a.y, b.y, acc);
+  acc = __dp4a(a.z, b.z, acc);
+  return __dp4a(a.w, b.w, acc);
+}
+
+struct MergeSlot {
+  float s;
+  int cell;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_t* __restrict__ f0_of,
+                const int32_t* __restrict__ f1_of, const int8_t* __restrict__ desc,
+                const uint32_t* __restrict__ vbits, const int32_t* __restrict__ q_patch,
+                const int32_t* __restrict__ q_count, int32_t* __restrict__ best_cell,
+                float* __restrict__ best_score, int* abort_flag) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;
+  uint8_t* sA = sB + kBStages * kBStageBytes;
+  uint32_t* sV = reinterpret_cast<uint32_t*>(sA + kAStages * kAStageBytes);
+  MergeSlot* sM = reinterpret_cast<MergeSlot*>(sV + kAStages * g.vwords);   // [2][kTileQ]
+
+  __shared__ uint64_t bar_full_b[kBStages], bar_empty_b[kBStages];
+  __shared__ uint64_t bar_full_a[kAStages], bar_empty_a[kAStages];
+  __shared__ uint64_t bar_acc_full[kAccStages], bar_acc_empty[kAccStages];
+  __shared__ uint32_t s_tmem_base;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kBStages; i++) { mbar_init(smem_u32(&bar_full_b[i]), 1); mbar_init(smem_u32(&bar_empty_b[i]), 1); }
+    for (int i = 0; i < kAStages; i++) {
+      mbar_init(smem_u32(&bar_full_a[i]), kGatherThreads);
+      mbar_init(smem_u32(&bar_empty_a[i]), 1 + kEpiWarps);
+    }
+    for (int i = 0; i < kAccStages; i++) { mbar_init(smem_u32(&bar_acc_full[i]), 1); mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmap);
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(&s_tmem_base), kAccStages * kAccCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+  const uint32_t box_bytes = 64u * (uint32_t)g.rows * (uint32_t)g.cx;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    uint32_t chunk = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      if (lane == 0) {
+        for (int c = 0; c < t.n_chunks; c++, chunk++) {
+          const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
+          mbar_wait(smem_u32(&bar_empty_b[s]), ph ^ 1, abort_flag, 1);
+          mbar_expect_tx(smem_u32(&bar_full_b[s]), box_bytes);
+          tma_load_4d(smem_u32(sB + s * kBStageBytes), &tmap, smem_u32(&bar_full_b[s]), 0, 0, t.X0 + c * g.cx, t.f0);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = umma_idesc_s8(kTileQ, g.n_chunk);
+    uint32_t chunk = 0, tile = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      if (t.n_rows == 0) continue;
+      if (lane == 0) {
+        const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
+        mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 2);
+        const uint32_t a_addr = smem_u32(sA + a * kAStageBytes);
+        for (int c = 0; c < t.n_chunks; c++, chunk++) {
+          const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
+          const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
+          mbar_wait(smem_u32(&bar_acc_empty[acc]), accph ^ 1, abort_flag, 3);
+          mbar_wait(smem_u32(&bar_full_b[s]), ph, abort_flag, 4);
+          tc_fence_after();
+          const uint32_t b_addr = smem_u32(sB + s * kBStageBytes);
+          const uint32_t d_addr = tmem_base + acc * kAccCols;
+          umma_s8(d_addr, umma_desc_k_sw64(a_addr), umma_desc_k_sw64(b_addr), idesc, 0);
+          umma_s8(d_addr, umma_desc_k_sw64(a_addr + 32), umma_desc_k_sw64(b_addr + 32), idesc, 1);
+          umma_commit(smem_u32(&bar_empty_b[s]));
+          umma_commit(smem_u32(&bar_acc_full[acc]));
+        }
+        if (t.n_chunks > 0) umma_commit(smem_u32(&bar_empty_a[a]));
+        else mbar_arrive(smem_u32(&bar_empty_a[a]));
+      }
+      __syncwarp();
+      tile++;
+    }
+  } else if (warp < 4) {
+    // ------------------------------------------------------------ query gather
+    const int gt = threadIdx.x - 64;
+    uint32_t tile = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      if (t.n_rows == 0) continue;
+      const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
+      mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5);
+      uint8_t* dst = sA + a * kAStageBytes;
+#pragma unroll
+      for (int rr = 0; rr < 2; rr++) {
+        const int r = gt + rr * kGatherThreads;
+        int4 v[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+        if (r < t.n_rows) {
+          const int cell1 = q_patch[(size_t)t.f1 * g.top_n + t.q0 + r];
+          const int4* src = reinterpret_cast<const int4*>(desc + ((size_t)t.f1 * g.cells + cell1) * 256);
+#pragma unroll
+          for (int c = 0; c < 4; c++) v[c] = __ldg(src + c);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<int4*>(dst + sw64_offset(r, c)) = v[c];
+      }
+      // validity words of the tile's cell range (plus the overrun of the last chunk)
+      const int w_lo = (t.X0 * g.rows) >> 5;
+      const int w_hi = min(g.vwords - 1, (((t.X0 + t.n_chunks * g.cx) * g.rows + 63) >> 5) + 1);
+      const uint32_t* vsrc = vbits + (size_t)t.f0 * g.vwords;
+      uint32_t* vdst = sV + a * g.vwords;
+      for (int w = w_lo + gt; w <= w_hi; w += kGatherThreads) vdst[w - w_lo] = vsrc[w];
+      fence_proxy_async_smem();
+      mbar_arrive(smem_u32(&bar_full_a[a]));
+      tile++;
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue
+    const int ew = warp - 4;
+    const int qd = warp & 3;          // TMEM lane quadrant this warp may read
+    const int half = ew >> 2;         // which of the row's two threads
+    const int row = qd * 32 + lane;
+    uint32_t chunk = 0, tile = 0;
+    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      if (t.n_rows == 0) continue;
+      const int pair = item / g.tiles_per_pair;
+      const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
+      mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 6);
+      const uint32_t* sv = sV + a * g.vwords;
+      const int base_bit = ((t.X0 * g.rows) >> 5) << 5;
+
+      // ---- this row's query, its window and the 256-d leading candidates
+      const bool active = row < t.n_rows;
+      int x_lo = 0, x_hi = -1, y_lo = 0, y_hi = -1;
+      bool have = false;
+      float bs = 0.0f;
+      int bcell = -1;
+      int lead_end = -1;
+      int curmax = 0x7fffffff, flip = 0;
+      float den_f = 1.0f;
+      if (active) {
+        const int cell1 = q_patch[(size_t)t.f1 * g.top_n + t.q0 + row];
+        const int qx = cell1 / g.rows, qy = cell1 - qx * g.rows;
+        x_lo = max(qx + g.shift_x - g.radius, 0);
+        x_hi = min(qx + g.shift_x + g.radius, g.cols - 1);
+        y_lo = max(qy + g.shift_y - g.radius, 0);
+        y_hi = min(qy + g.shift_y + g.radius, g.rows - 1);
+        const int4* qp = reinterpret_cast<const int4*>(desc + ((size_t)t.f1 * g.cells + cell1) * 256);
+        const int8_t* d0 = desc + (size_t)t.f0 * g.cells * 256;
+        int n_cand = 0, nq256 = -1, nq64 = 0;
+        for (int x = x_lo; x <= x_hi && n_cand == 0 && y_hi >= y_lo; x++) {
+          int lo = x * g.rows + y_lo;
+          const int hi = x * g.rows + y_hi;
+          while (n_cand == 0) {
+            const int c = first_set_in_range(sv, base_bit, lo, hi);
+            if (c < 0) break;
+            const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)c * 256);
+            int dot = 0, nc = 0, nq = 0;
+#pragma unroll 4
+            for (int k = 0; k < 16; k++) {
+              const int4 cv = __ldg(cp + k), qv = __ldg(qp + k);
+              dot = dp4a4(cv, qv, dot);
+              nc = dp4a4(cv, cv, nc);
+              nq = dp4a4(qv, qv, nq);
+            }
+            nq256 = nq;
+            n_cand = nc;
+            const float s = wrapped_cos2(dot, nc, nq256);
+            if (s > g.accept_gt && (!have || s > bs)) { have = true; bs = s; bcell = c; }
+            lead_end = c;
+            lo = c + 1;
+          }
+        }
+        if (n_cand != 0) {
+#pragma unroll
+          for (int k = 0; k < 4; k++) { const int4 qv = __ldg(qp + k); nq64 = dp4a4(qv, qv, nq64); }
+          const int den_i = (int)((unsigned)n_cand * (unsigned)nq64);
+          den_f = __int2float_rn(den_i);
+          // conservative start of the key filter: every key <= curmax has s <= accept_gt
+          if (den_i > 0) {
+            const double b = floor((double)g.accept_gt * (double)den_f) - 256.0;
+            curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
+          } else if (den_i < 0) {
+            flip = -1;
+            const double b = -ceil((double)g.accept_gt * (double)den_f) - 257.0;
+            curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
+          } else {
+            curmax = 0;   // s = +inf only for n > 0
+          }
+        }
+        // n_cand == 0: every valid candidate had a zero norm and was evaluated above
+      }
+
+      // ---- the tile's chunks
+      for (int c = 0; c < t.n_chunks; c++, chunk++) {
+        const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
+        mbar_wait(smem_u32(&bar_acc_full[acc]), accph, abort_flag, 7);
+        tc_fence_after();
+        const int chunk_cell = (t.X0 + c * g.cx) * g.rows;
+        const int col_limit = g.cx * g.rows;
+        int x0b = t.X0 + c * g.cx, y0b = 0;   // cell coordinates of column `col`
+        int col = 0;
+        // this thread's blocks: half, half+2, ...
+        if (half) { y0b = 32; while (y0b >= g.rows) { y0b -= g.rows; x0b++; } col = 32; }
+        for (; col < col_limit; col += 64) {
+          const int cb = chunk_cell + col;
+          // validity of the block's 32 cells (uniform), minus the padding columns
+          const int o = cb - base_bit;
+          uint32_t vm = __funnelshift_r(sv[o >> 5], sv[(o >> 5) + 1], o & 31);
+          if (col_limit - col < 32) vm &= (1u << (col_limit - col)) - 1u;
+          // this row's window inside the block
+          uint32_t wm = 0;
+          {
+            int x = x0b, off = -y0b;
+            while (off < 32) {
+              if (x >= x_lo && x <= x_hi) {
+                const int lo = max(off + y_lo, 0), hi = min(off + y_hi, 31);
+                if (lo <= hi) wm |= (0xffffffffu >> (31 - (hi - lo))) << lo;
+              }
+              x++;
+              off += g.rows;
+            }
+          }
+          uint32_t m = wm & vm;
+          if (lead_end >= cb) m = (lead_end - cb >= 31) ? 0u : (m & ~((2u << (lead_end - cb)) - 1u));
+          if (__any_sync(0xffffffffu, m != 0)) {
+            int v[32];
+            tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + acc * kAccCols + col, v);
+            tmem_ld_wait();
+            if (m != 0) {
+#pragma unroll
+              for (int j = 0; j < 32; j++) {
+                if ((m >> j) & 1u) {
+                  const int n = (int)((unsigned)v[j] * (unsigned)v[j]);
+                  const int key = n ^ flip;
+                  if (key > curmax) {
+                    curmax = key;
+                    const float s = __fdiv_rn(__int2float_rn(n), den_f);
+                    if (s > g.accept_gt && (!have || s > bs)) { have = true; bs = s; bcell = cb + j; }
+                  }
+                }
+              }
+            }
+          }
+          y0b += 64;
+          while (y0b >= g.rows) { y0b -= g.rows; x0b++; }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
+      }
+
+      // ---- merge the row's two threads: larger score, ties to the earlier cell
+      MergeSlot* mslot = sM + (tile & 1) * kTileQ + row;
+      if (half == 1) { mslot->s = bs; mslot->cell = have ? bcell : -1; }
+      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
+      if (half == 0 && active) {
+        const float os = mslot->s;
+        const int oc = mslot->cell;
+        if (oc >= 0 && (!have || os > bs || (os == bs && oc < bcell))) { have = true; bs = os; bcell = oc; }
+        const size_t out = (size_t)pair * g.top_n + t.q0 + row;
+        best_cell[out] = have ? bcell : -1;
+        best_score[out] = bs;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bar_empty_a[a]));
+      tile++;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
+}
+
+}  // namespace
+
+mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs, int top_n,
+                             const int32_t* d_f0, const int32_t* d_f1, const int8_t* d_desc,
+                             const int32_t* d_max_idx, const float* d_prob, const int32_t* d_q_patch,
+                             const int32_t* d_q_count, int32_t* d_best_cell, float* d_best_score) {
+  if (n_frames <= 0) MV_BAD_ARG(ctx, "tensor-core matcher: n_frames must be given");
+  if (p->rows > 256) MV_BAD_ARG(ctx, "tensor-core matcher: rows <= 256 (one cell column per TMA box row block)");
+  const double thr2 = p->match_threshold * p->match_threshold;
+  if (!(thr2 >= 0.0)) MV_BAD_ARG(ctx, "tensor-core matcher: match_threshold^2 must be >= 0");
+  mv_tmap_encode_fn encode = mv_get_tmap_encode();
+  if (!encode) {
+    snprintf(ctx->err, sizeof(ctx->err), "cuTensorMapEncodeTiled not available from the driver");
+    return MV_ERR_CUDA;
+  }
+  TcGeom g;
+  g.rows = p->rows; g.cols = p->cols; g.cells = p->rows * p->cols;
+  g.shift_x = p->shift_x; g.shift_y = p->shift_y; g.radius = p->radius; g.top_n = top_n;
+  g.cx = 256 / p->rows;
+  if (g.cx > p->cols) g.cx = p->cols;
+  g.n_chunk = (g.cx * p->rows + 15) & ~15;
+  g.vwords = (g.cells + 31) / 32 + kVPadWords + (g.cx * p->rows + 31) / 32;
+  g.tiles_per_pair = (top_n + kTileQ - 1) / kTileQ;
+  g.n_items = n_pairs * g.tiles_per_pair;
+  g.accept_gt = mv_round_down(thr2);
+  g.prob_lt = mv_round_up(p->min_prob0);
+
+  void* vb = nullptr; void* flag = nullptr;
+  mv_status st = mv_scratch(ctx, "match.vbits", sizeof(uint32_t) * (size_t)n_frames * g.vwords, &vb);
+  if (st) return st;
+  st = mv_scratch(ctx, "match.tc_abort", 256, &flag);
+  if (st) return st;
+
+  CUtensorMap tmap;
+  const cuuint64_t dims[4] = {256, (cuuint64_t)p->rows, (cuuint64_t)p->cols, (cuuint64_t)n_frames};
+  const cuuint64_t strides[3] = {256, (cuuint64_t)p->rows * 256, (cuuint64_t)g.cells * 256};
+  const cuuint32_t box[4] = {64, (cuuint32_t)p->rows, (cuuint32_t)g.cx, 1};
+  const cuuint32_t es[4] = {1, 1, 1, 1};
+  const CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 4, const_cast<int8_t*>(d_desc), dims, strides, box,
+                             es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    snprintf(ctx->err, sizeof(ctx->err), "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return MV_ERR_CUDA;
+  }
+
+  mv_prof_scope ps(ctx, "match");
+  MV_CUDA(ctx, cudaMemsetAsync(vb, 0, sizeof(uint32_t) * (size_t)n_frames * g.vwords, ctx->stream));
+  MV_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
+  {
+    dim3 grid((g.cells + 255) / 256, n_frames);
+    valid_bits_kernel<<<grid, 256, 0, ctx->stream>>>(g.cells, g.vwords, g.prob_lt, d_max_idx, d_prob, (uint32_t*)vb);
+    MV_CHECK_LAUNCH(ctx);
+  }
+  const size_t smem = 1024 + (size_t)kBStages * kBStageBytes + (size_t)kAStages * kAStageBytes +
+                      sizeof(uint32_t) * (size_t)kAStages * g.vwords + sizeof(MergeSlot) * 2 * kTileQ;
+  if (smem > 227 * 1024) MV_BAD_ARG(ctx, "tensor-core matcher: grid too large for the shared-memory validity window");
+  MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;
+  match_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(tmap, g, d_f0, d_f1, d_desc, (const uint32_t*)vb, d_q_patch,
+                                                        d_q_count, d_best_cell, d_best_score, (int*)flag);
+  MV_CHECK_LAUNCH(ctx);
+  return MV_OK;
 }

@@ -108,20 +108,26 @@ def _oracle_pair(oracle, rows, cols, s0, d0, s1, d1, N, M, radius=4, shift=(4, 4
     (24, 80, 300, 200, 256, 30, (-3, 5)),        # window larger than the grid in y
     (24, 80, 300, 200, 256, 0, (1, 1)),          # single-cell window
     (24, 80, 300, 200, 256, 2, (200, 0)),        # window entirely off-grid: no matches
+    (94, 310, 550, 16000, 16384, 16, (4, 4)),    # BASELINE configs[4] shape: 16k keypoints, 33x33 window
+    (94, 155, 550, 8000, 8192, 4, (4, 4)),       # configs[1] sweep, 8k keypoints
+    (13, 300, 300, 500, 512, 5, (-2, 1)),        # short columns: a 32-cell block spans 3+ cell columns
+    (200, 40, 300, 700, 1024, 6, (2, -3)),       # tall columns: one cell column per TMA box
 ])
-def test_match_pair_vs_oracle(tk, oracle, synth, rows, cols, permille, N, M, radius, shift):
+@pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
+def test_match_pair_vs_oracle(tk, oracle, synth, rows, cols, permille, N, M, radius, shift, tc):
     off = synth.default_offsets(2, 21)
     s0, d0, _ = synth.synth_frame(21, rows, cols, 0, int(off[0, 0]), int(off[0, 1]), permille)
     s1, d1, _ = synth.synth_frame(21, rows, cols, 1, int(off[1, 0]), int(off[1, 1]), permille)
     idx, pr, pa, ix, ref = _oracle_pair(oracle, rows, cols, s0, d0, s1, d1, N, M, radius, shift, synth.SEMI_SCALE)
-    p = tk.match_params(rows, cols, shift[0], shift[1], radius, M)
+    p = tk.match_params(rows, cols, shift[0], shift[1], radius, M, use_tensor_cores=tc)
     got = tk.match_pair(p, d0, d1, idx, pr, pa, ix)
     assert got["n"] == ref["n"]
     assert (got["pts0"] == ref["pts0"]).all() and (got["pts1"] == ref["pts1"]).all()
     assert (got["cell0"] == ref["cell0"]).all() and (bits(got["score"]) == bits(ref["score"])).all()
 
 
-def test_match_zero_descriptors_and_ties(tk, oracle, synth):
+@pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
+def test_match_zero_descriptors_and_ties(tk, oracle, synth, tc):
     rows, cols = 24, 80
     s0, d0, _ = synth.synth_frame(2, rows, cols, 0, 0, 0, 400)
     s1, d1, _ = synth.synth_frame(2, rows, cols, 1, 4, 4, 400)
@@ -129,24 +135,26 @@ def test_match_zero_descriptors_and_ties(tk, oracle, synth):
     d0[::2] = 0                       # sticky zero norm: several leading candidates go the 256-d way
     d0[1::4] = d0[1]                  # identical descriptors: exact score ties, first must win
     idx, pr, pa, ix, ref = _oracle_pair(oracle, rows, cols, s0, d0, s1, d1, 100, 150, scale=synth.SEMI_SCALE)
-    got = tk.match_pair(tk.match_params(rows, cols), d0, d1, idx, pr, pa, ix)
+    got = tk.match_pair(tk.match_params(rows, cols, use_tensor_cores=tc), d0, d1, idx, pr, pa, ix)
     assert got["n"] == ref["n"] > 0
     assert (got["cell0"] == ref["cell0"]).all() and (bits(got["score"]) == bits(ref["score"])).all()
     assert (got["pts0"] == ref["pts0"]).all()
 
 
-def test_match_self_pair_golden(tk, image0, kat):
+@pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
+def test_match_self_pair_golden(tk, image0, kat, tc):
     idx, pr, _ = tk.compute_softmax(image0["semi_scale"], image0["semi"], legacy=True)
     pa, ix, _ = tk.compute_top_N(image0["semi_scale"], image0["semi"], 100, legacy=True)
-    got = tk.match_pair(tk.match_params(24, 80), image0["desc"], image0["desc"], idx, pr, pa, ix)
+    got = tk.match_pair(tk.match_params(24, 80, use_tensor_cores=tc), image0["desc"], image0["desc"], idx, pr, pa, ix)
     assert got["n"] == 93
     assert (got["pts0"] == kat["self_pts0"]).all() and (got["pts1"] == kat["self_pts1"]).all()
 
 
-def test_match_no_queries(tk, synth):
+@pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
+def test_match_no_queries(tk, synth, tc):
     s0, d0, _ = synth.synth_frame(2, 24, 80, 0, 0, 0)
     idx, pr, _ = tk.compute_softmax(float(synth.SEMI_SCALE), s0)
-    got = tk.match_pair(tk.match_params(24, 80), d0, d0, idx, pr, np.zeros(0, np.int32), np.zeros(0, np.int32))
+    got = tk.match_pair(tk.match_params(24, 80, use_tensor_cores=tc), d0, d0, idx, pr, np.zeros(0, np.int32), np.zeros(0, np.int32))
     assert got["n"] == 0
 
 
@@ -294,6 +302,21 @@ def test_track_sequence_vs_oracle(tracker, tk, oracle, synth, rows, cols, N, M, 
         assert got["pnp_inliers"] == ref.pnp_inliers
         assert rot_angle(got["q"], np.array(list(ref.q))) < 1e-5
         assert np.linalg.norm(got["t"] - np.array(list(ref.t))) <= 1e-5 * max(1.0, np.linalg.norm(list(ref.t)))
+
+
+def test_track_sequence_tensor_core_matcher_same_bytes(tracker, tk, synth):
+    """The tcgen05 matcher inside the whole path: byte-identical result records, many tiles per CTA."""
+    import torch
+    rows, cols, n_frames, seed = 47, 155, 40, 3
+    off = synth.default_offsets(n_frames, seed)
+    semi, desc, depth = tracker.synth_frames(seed, rows, cols, 0, off)
+    scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+    out = []
+    for tc in (False, True):
+        p = tk.track_params(rows, cols, top_n=1000, max_valid=8192, max_matches=1024, hypotheses=32,
+                            use_tensor_cores=tc)
+        out.append(tk.results_to_numpy(tracker.track_sequence(p, semi, scale, desc, depth)).tobytes())
+    assert out[0] == out[1]
 
 
 def test_track_legacy_symbol(tk, image0, kat):
