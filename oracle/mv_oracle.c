@@ -574,17 +574,19 @@ static void ne_add_point(ne_acc* acc, const float R[9], const float t[3], const 
   float xc = fmaf(R[2], Z, fmaf(R[1], Y, fmaf(R[0], X, t[0])));
   float yc = fmaf(R[5], Z, fmaf(R[4], Y, fmaf(R[3], X, t[1])));
   float zc = fmaf(R[8], Z, fmaf(R[7], Y, fmaf(R[6], X, t[2])));
-  int ok = zc > c->min_depth;
+  int ok = zc > c->min_depth && zc < 1e30f;   /* depth gate: in front of the camera and finite */
   float iz = ok ? 1.0f / zc : 0.0f;
   float a = xc * iz, b = yc * iz;
-  float ru = fmaf(c->fx, a, c->cx) - u;
-  float rv = fmaf(c->fy, b, c->cy) - v;
+  float ncu = c->cx - u, ncv = c->cy - v;   /* rounded once, when a correspondence is staged */
+  float ru = fmaf(c->fx, a, ncu);
+  float rv = fmaf(c->fy, b, ncv);
   float e2 = fmaf(rv, rv, ru * ru);
   int w = ok && (!gated || e2 < c->gate_sq);
   float fx = w ? c->fx : 0.0f, fy = w ? c->fy : 0.0f;
   float fxa = fx * a, fyb = fy * b, fiz = fx * iz, giz = fy * iz;
-  float u0 = -(fxa * b), u1 = fmaf(fxa, a, fx), u2 = -(fx * b), u3 = fiz, u5 = -(fiz * a);
-  float v0 = -fmaf(fyb, b, fy), v1 = fyb * a, v2 = fy * a, v4 = giz, v5 = -(giz * b);
+  float na = -a, nb = -b, nfy = -fy;
+  float u0 = fxa * nb, u1 = fmaf(fxa, a, fx), u2 = fx * nb, u3 = fiz, u5 = fiz * na;
+  float v0 = fmaf(fyb, nb, nfy), v1 = fyb * a, v2 = fy * a, v4 = giz, v5 = giz * nb;
   float* H = acc->H;
   /* row 0 */
   H[0] = fmaf(v0, v0, fmaf(u0, u0, H[0]));

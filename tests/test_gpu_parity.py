@@ -214,17 +214,19 @@ def test_matmul_shim(tk, kat):
 
 
 # ------------------------------------------------------------------ Gauss-Newton PnP
-def _pnp_params(tk, H, lanes, seed=0, refine=10):
+def _pnp_params(tk, H, lanes, seed=0, refine=10, sample_size=8):
     from maveric_slam_b200 import lib
     p = lib.PnpParams()
     lib.load().mv_pnp_params_default(C.byref(p))
     p.hypotheses, p.lanes_per_hypothesis, p.seed, p.refine_iters = H, lanes, seed, refine
+    p.sample_size = sample_size
     return p
 
 
-@pytest.mark.parametrize("lanes", [1, 4, 8, 32])
-@pytest.mark.parametrize("n,stride", [(1000, 1024), (37, 64), (1500, 1536), (8, 8)])
-def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, n, stride):
+# lanes = 2 is the packed-FP32 (FFMA2) single-thread form; the others are LANES threads per hypothesis
+@pytest.mark.parametrize("lanes,sample_size", [(1, 8), (2, 8), (2, 7), (4, 8), (8, 8), (32, 8)])
+@pytest.mark.parametrize("n,stride", [(1000, 1024), (37, 64), (1500, 1536), (2049, 2304), (8, 8)])
+def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, sample_size, n, stride):
     import torch
     H, P = 96, 3
     corr = np.zeros((P, 5, stride), np.float32)
@@ -234,11 +236,11 @@ def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, n, stride):
         corr[p] = c
         truth.append(pose)
     cnt = np.full(P, n, np.int32)
-    prm = _pnp_params(tk, H, lanes, seed=4)
+    prm = _pnp_params(tk, H, lanes, seed=4, sample_size=sample_size)
     pose, stats, hyp = tracker.pnp_gn(prm, torch.from_numpy(corr).to(tracker.device),
                                       torch.from_numpy(cnt).to(tracker.device), want_hyp=True)
     pose, stats, hyp = pose.cpu().numpy(), stats.cpu().numpy(), hyp.cpu().numpy()
-    cfg = orc.pnp_cfg(hypotheses=H, seed=4, lanes=lanes)
+    cfg = orc.pnp_cfg(hypotheses=H, seed=4, lanes=lanes, sample_size=sample_size)
     for p in range(P):
         rp, rs, rh = oracle.pnp_gn(cfg, corr[p], n, pair_index=p, want_hyp=True)
         # per hypothesis: same inlier count, pose within tolerance
