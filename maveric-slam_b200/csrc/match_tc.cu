@@ -12,15 +12,19 @@
 //               descriptor tensor per chunk, SWIZZLE_64B, into a 6-deep shared-memory ring
 //   warp 1      MMA issuer: per chunk two tcgen05.mma.kind::i8 (M=128, N=Cx*rows<=256, K=32)
 //               into one of two 256-column TMEM accumulator stages
-//   warps 2-3   query gather: the first 64 bytes of the tile's 128 query descriptors into the
-//               A operand (same swizzle), and the validity bits of the tile's cell range
-//   warps 4-11  epilogue, thread <-> query row (TMEM lane), two threads per row splitting the
-//               32-column blocks: tcgen05.ld, window/validity mask, and the reference's exact
-//               score only for the rare element that can still win (see "filter" below)
+//   warps 2-5   query warps, thread <-> query row, one tile ahead of the epilogue: the first 64
+//               bytes of the query descriptor into the A operand (same swizzle), the validity
+//               bits of the tile's cell range, and the query's leading 256-dimension
+//               evaluation (squared_dist's first call, tracking_main.c:21-32, sticky while the
+//               candidate norm is 0) with dp4a -- its global-load latency hides behind the
+//               previous tile's epilogue; the per-row state goes to shared memory
+//   warps 6-13  epilogue, thread <-> query row (TMEM lane), two threads per row splitting the
+//               32-column blocks: tcgen05.ld, then a BRANCH-FREE pass that squares each
+//               accumulator, applies window/validity mask and key filter and collects the
+//               few survivors in a bitmask; only survivors take the reference's exact float
+//               path (see "filter" below), re-read one TMEM column at a time
 //
-// The distance matrix never leaves TMEM.  The one 256-dimension evaluation per query
-// (squared_dist's first call, tracking_main.c:21-32, sticky while the candidate norm is 0) is
-// done by the epilogue thread with dp4a before the tile's chunks arrive.
+// The distance matrix never leaves TMEM.
 //
 // Filter.  For the non-leading candidates of a query the score (tracking_main.c:154) is
 //     s = float(int32(dot*dot)) / float(int32(norm_F * norm_q64))
@@ -45,9 +49,11 @@ constexpr int kAStages = 2;
 constexpr int kAStageBytes = kTileQ * 64;
 constexpr int kAccStages = 2;
 constexpr int kAccCols = 256;
-constexpr int kGatherThreads = 64;
+constexpr int kQueryWarps = 4;
+constexpr int kQueryThreads = 32 * kQueryWarps;     // == kTileQ: one thread per query row
+constexpr int kEpiWarp0 = 2 + kQueryWarps;
 constexpr int kEpiWarps = 8;
-constexpr int kThreads = 32 * (4 + kEpiWarps);
+constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr int kVPadWords = 12;   // zero words after a frame's validity bits (chunk overrun + funnel)
 
 struct TcGeom {
@@ -138,6 +144,18 @@ struct MergeSlot {
   int cell;
 };
 
+// Per-row state the query warps hand to the epilogue (32 bytes).
+struct __align__(16) RowInfo {
+  int xwin;       // x_lo | x_hi << 16   (x_hi < x_lo: empty window / inactive row)
+  int ywin;       // y_lo | y_hi << 16
+  int lead_end;   // last cell scored over 256 dims (-1: none)
+  int bcell;      // best so far (-1: none)
+  float bs;       // its score
+  float den_f;    // float(int32(norm_F * norm_q64)), the denominator of every later score
+  int curmax;     // start of the key filter
+  int flip;       // 0 / -1: key = n ^ flip
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_t* __restrict__ f0_of,
                 const int32_t* __restrict__ f1_of, const int8_t* __restrict__ desc,
@@ -148,8 +166,10 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
   uint8_t* sA = sB + kBStages * kBStageBytes;
-  uint32_t* sV = reinterpret_cast<uint32_t*>(sA + kAStages * kAStageBytes);
-  MergeSlot* sM = reinterpret_cast<MergeSlot*>(sV + kAStages * g.vwords);   // [2][kTileQ]
+  uint32_t* sV = reinterpret_cast<uint32_t*>(sA + kAStages * kAStageBytes);   // [kAStages][vstride]
+  const int vstride = (g.vwords + 3) & ~3;
+  RowInfo* sR = reinterpret_cast<RowInfo*>(sV + kAStages * ((g.vwords + 3) & ~3));   // [kAStages][kTileQ]
+  MergeSlot* sM = reinterpret_cast<MergeSlot*>(sR + kAStages * kTileQ);              // [2][kTileQ]
 
   __shared__ uint64_t bar_full_b[kBStages], bar_empty_b[kBStages];
   __shared__ uint64_t bar_full_a[kAStages], bar_empty_a[kAStages];
@@ -161,7 +181,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
   if (threadIdx.x == 0) {
     for (int i = 0; i < kBStages; i++) { mbar_init(smem_u32(&bar_full_b[i]), 1); mbar_init(smem_u32(&bar_empty_b[i]), 1); }
     for (int i = 0; i < kAStages; i++) {
-      mbar_init(smem_u32(&bar_full_a[i]), kGatherThreads);
+      mbar_init(smem_u32(&bar_full_a[i]), kQueryThreads);
       mbar_init(smem_u32(&bar_empty_a[i]), 1 + kEpiWarps);
     }
     for (int i = 0; i < kAccStages; i++) { mbar_init(smem_u32(&bar_acc_full[i]), 1); mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps); }
@@ -223,42 +243,125 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       __syncwarp();
       tile++;
     }
-  } else if (warp < 4) {
-    // ------------------------------------------------------------ query gather
-    const int gt = threadIdx.x - 64;
+  } else if (warp < kEpiWarp0) {
+    // ------------------------------------------------------------ query warps (one tile ahead)
+    const int row = threadIdx.x - 64;
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
       const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
       if (t.n_rows == 0) continue;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
       mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5);
-      uint8_t* dst = sA + a * kAStageBytes;
-#pragma unroll
-      for (int rr = 0; rr < 2; rr++) {
-        const int r = gt + rr * kGatherThreads;
-        int4 v[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
-        if (r < t.n_rows) {
-          const int cell1 = q_patch[(size_t)t.f1 * g.top_n + t.q0 + r];
-          const int4* src = reinterpret_cast<const int4*>(desc + ((size_t)t.f1 * g.cells + cell1) * 256);
-#pragma unroll
-          for (int c = 0; c < 4; c++) v[c] = __ldg(src + c);
-        }
-#pragma unroll
-        for (int c = 0; c < 4; c++) *reinterpret_cast<int4*>(dst + sw64_offset(r, c)) = v[c];
-      }
+
       // validity words of the tile's cell range (plus the overrun of the last chunk)
       const int w_lo = (t.X0 * g.rows) >> 5;
       const int w_hi = min(g.vwords - 1, (((t.X0 + t.n_chunks * g.cx) * g.rows + 63) >> 5) + 1);
       const uint32_t* vsrc = vbits + (size_t)t.f0 * g.vwords;
-      uint32_t* vdst = sV + a * g.vwords;
-      for (int w = w_lo + gt; w <= w_hi; w += kGatherThreads) vdst[w - w_lo] = vsrc[w];
+      uint32_t* sv = sV + a * vstride;
+      for (int w = w_lo + row; w <= w_hi; w += kQueryThreads) sv[w - w_lo] = vsrc[w];
+      const int base_bit = w_lo << 5;
+
+      // this row's query: A operand row and search window
+      const bool active = row < t.n_rows;
+      int cell1 = 0, x_lo = 0, x_hi = -1, y_lo = 0, y_hi = -1;
+      int4 q4[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
+      if (active) {
+        cell1 = q_patch[(size_t)t.f1 * g.top_n + t.q0 + row];
+        const int qx = cell1 / g.rows, qy = cell1 - qx * g.rows;
+        x_lo = max(qx + g.shift_x - g.radius, 0);
+        x_hi = min(qx + g.shift_x + g.radius, g.cols - 1);
+        y_lo = max(qy + g.shift_y - g.radius, 0);
+        y_hi = min(qy + g.shift_y + g.radius, g.rows - 1);
+        if (y_hi < y_lo) { x_lo = 0; x_hi = -1; }
+      }
+      const int4* qp = reinterpret_cast<const int4*>(desc + ((size_t)t.f1 * g.cells + cell1) * 256);
+      if (active) {
+#pragma unroll
+        for (int c = 0; c < 4; c++) q4[c] = __ldg(qp + c);
+      }
+      {
+        uint8_t* dst = sA + a * kAStageBytes;
+#pragma unroll
+        for (int c = 0; c < 4; c++) *reinterpret_cast<int4*>(dst + sw64_offset(row, c)) = q4[c];
+      }
+      asm volatile("bar.sync 2, %0;" ::"n"(kQueryThreads) : "memory");   // validity words visible
+
+      // Leading candidates (tracking_main.c:21-32): every valid window cell, in scan order, is
+      // scored over 256 dims until one has a non-zero norm.  The search for the next cell is
+      // per lane; the evaluation is warp-convergent so each round is one batch of loads.
+      RowInfo ri;
+      ri.xwin = (x_lo & 0xffff) | (x_hi << 16);
+      ri.ywin = (y_lo & 0xffff) | (y_hi << 16);
+      ri.lead_end = -1; ri.bcell = -1; ri.bs = 0.0f; ri.den_f = 1.0f; ri.curmax = 0x7fffffff; ri.flip = 0;
+      {
+        const int8_t* d0 = desc + (size_t)t.f0 * g.cells * 256;
+        int n_cand = 0, nq64 = 0;
+        int sx = x_lo, slo = x_lo * g.rows + y_lo;   // search cursor: column and first cell to test
+        bool searching = x_hi >= x_lo;
+        while (true) {
+          int c = -1;
+          while (searching && c < 0) {
+            c = first_set_in_range(sv, base_bit, slo, sx * g.rows + y_hi);
+            if (c < 0) {
+              sx++;
+              slo = sx * g.rows + y_lo;
+              searching = sx <= x_hi;
+            }
+          }
+          if (!__any_sync(0xffffffffu, c >= 0)) break;
+          if (c >= 0) {
+            const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)c * 256);
+            int dot = 0, nc = 0, nq = 0;
+#pragma unroll
+            for (int kb = 0; kb < 16; kb += 8) {
+              int4 cv[8], qv[8];
+#pragma unroll
+              for (int k = 0; k < 8; k++) { cv[k] = __ldg(cp + kb + k); qv[k] = __ldg(qp + kb + k); }
+#pragma unroll
+              for (int k = 0; k < 8; k++) {
+                dot = dp4a4(cv[k], qv[k], dot);
+                nc = dp4a4(cv[k], cv[k], nc);
+                nq = dp4a4(qv[k], qv[k], nq);
+                if (kb == 0 && k == 3) nq64 = nq;
+              }
+            }
+            n_cand = nc;
+            const float s = wrapped_cos2(dot, nc, nq);
+            if (s > g.accept_gt && (ri.bcell < 0 || s > ri.bs)) { ri.bs = s; ri.bcell = c; }
+            ri.lead_end = c;
+            slo = c + 1;
+            searching = n_cand == 0;   // sticky zero norm: the next valid cell is a leading one too
+          }
+        }
+        if (n_cand != 0) {
+          const int den_i = (int)((unsigned)n_cand * (unsigned)nq64);
+          ri.den_f = __int2float_rn(den_i);
+          // conservative start of the key filter: every key <= curmax has s <= accept_gt
+          if (den_i > 0) {
+            const double b = floor((double)g.accept_gt * (double)ri.den_f) - 256.0;
+            ri.curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
+          } else if (den_i < 0) {
+            ri.flip = -1;
+            const double b = -ceil((double)g.accept_gt * (double)ri.den_f) - 257.0;
+            ri.curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
+          } else {
+            ri.curmax = 0;   // s = +inf only for n > 0
+          }
+        }
+        // n_cand == 0: every valid candidate had a zero norm and was scored above
+      }
+      {
+        int4* rdst = reinterpret_cast<int4*>(sR + a * kTileQ + row);
+        rdst[0] = make_int4(ri.xwin, ri.ywin, ri.lead_end, ri.bcell);
+        rdst[1] = make_int4(__float_as_int(ri.bs), __float_as_int(ri.den_f), ri.curmax, ri.flip);
+      }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full_a[a]));
       tile++;
     }
   } else {
     // ------------------------------------------------------------ epilogue
-    const int ew = warp - 4;
+    const int ew = warp - kEpiWarp0;
     const int qd = warp & 3;          // TMEM lane quadrant this warp may read
     const int half = ew >> 2;         // which of the row's two threads
     const int row = qd * 32 + lane;
@@ -269,69 +372,26 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       const int pair = item / g.tiles_per_pair;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
       mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 6);
-      const uint32_t* sv = sV + a * g.vwords;
+      const uint32_t* sv = sV + a * vstride;
       const int base_bit = ((t.X0 * g.rows) >> 5) << 5;
 
-      // ---- this row's query, its window and the 256-d leading candidates
       const bool active = row < t.n_rows;
-      int x_lo = 0, x_hi = -1, y_lo = 0, y_hi = -1;
-      bool have = false;
-      float bs = 0.0f;
-      int bcell = -1;
-      int lead_end = -1;
-      int curmax = 0x7fffffff, flip = 0;
-      float den_f = 1.0f;
-      if (active) {
-        const int cell1 = q_patch[(size_t)t.f1 * g.top_n + t.q0 + row];
-        const int qx = cell1 / g.rows, qy = cell1 - qx * g.rows;
-        x_lo = max(qx + g.shift_x - g.radius, 0);
-        x_hi = min(qx + g.shift_x + g.radius, g.cols - 1);
-        y_lo = max(qy + g.shift_y - g.radius, 0);
-        y_hi = min(qy + g.shift_y + g.radius, g.rows - 1);
-        const int4* qp = reinterpret_cast<const int4*>(desc + ((size_t)t.f1 * g.cells + cell1) * 256);
-        const int8_t* d0 = desc + (size_t)t.f0 * g.cells * 256;
-        int n_cand = 0, nq256 = -1, nq64 = 0;
-        for (int x = x_lo; x <= x_hi && n_cand == 0 && y_hi >= y_lo; x++) {
-          int lo = x * g.rows + y_lo;
-          const int hi = x * g.rows + y_hi;
-          while (n_cand == 0) {
-            const int c = first_set_in_range(sv, base_bit, lo, hi);
-            if (c < 0) break;
-            const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)c * 256);
-            int dot = 0, nc = 0, nq = 0;
-#pragma unroll 4
-            for (int k = 0; k < 16; k++) {
-              const int4 cv = __ldg(cp + k), qv = __ldg(qp + k);
-              dot = dp4a4(cv, qv, dot);
-              nc = dp4a4(cv, cv, nc);
-              nq = dp4a4(qv, qv, nq);
-            }
-            nq256 = nq;
-            n_cand = nc;
-            const float s = wrapped_cos2(dot, nc, nq256);
-            if (s > g.accept_gt && (!have || s > bs)) { have = true; bs = s; bcell = c; }
-            lead_end = c;
-            lo = c + 1;
-          }
-        }
-        if (n_cand != 0) {
+      const int4 r0 = reinterpret_cast<const int4*>(sR + a * kTileQ + row)[0];
+      const int4 r1 = reinterpret_cast<const int4*>(sR + a * kTileQ + row)[1];
+      const int x_lo = r0.x & 0xffff, x_hi = r0.x >> 16, y_lo = r0.y & 0xffff, y_hi = r0.y >> 16;
+      const int lead_end = r0.z;
+      int bcell = r0.w;
+      float bs = __int_as_float(r1.x);
+      const float den_f = __int_as_float(r1.y);
+      int curmax = r1.z;
+      const int flip = r1.w;
+      // warp-uniform column range of this warp's windows (blocks outside it are skipped outright)
+      int wx_lo = x_hi >= x_lo ? x_lo : (1 << 20);
+      int wx_hi = x_hi >= x_lo ? x_hi : -1;
 #pragma unroll
-          for (int k = 0; k < 4; k++) { const int4 qv = __ldg(qp + k); nq64 = dp4a4(qv, qv, nq64); }
-          const int den_i = (int)((unsigned)n_cand * (unsigned)nq64);
-          den_f = __int2float_rn(den_i);
-          // conservative start of the key filter: every key <= curmax has s <= accept_gt
-          if (den_i > 0) {
-            const double b = floor((double)g.accept_gt * (double)den_f) - 256.0;
-            curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
-          } else if (den_i < 0) {
-            flip = -1;
-            const double b = -ceil((double)g.accept_gt * (double)den_f) - 257.0;
-            curmax = b < -2147483648.0 ? (int)0x80000000 : (b > 2147483647.0 ? 0x7fffffff : (int)b);
-          } else {
-            curmax = 0;   // s = +inf only for n > 0
-          }
-        }
-        // n_cand == 0: every valid candidate had a zero norm and was evaluated above
+      for (int o = 16; o; o >>= 1) {
+        wx_lo = min(wx_lo, __shfl_xor_sync(0xffffffffu, wx_lo, o));
+        wx_hi = max(wx_hi, __shfl_xor_sync(0xffffffffu, wx_hi, o));
       }
 
       // ---- the tile's chunks
@@ -339,13 +399,18 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
         mbar_wait(smem_u32(&bar_acc_full[acc]), accph, abort_flag, 7);
         tc_fence_after();
-        const int chunk_cell = (t.X0 + c * g.cx) * g.rows;
+        const int chunk_x0 = t.X0 + c * g.cx;
+        const int chunk_cell = chunk_x0 * g.rows;
         const int col_limit = g.cx * g.rows;
-        int x0b = t.X0 + c * g.cx, y0b = 0;   // cell coordinates of column `col`
-        int col = 0;
-        // this thread's blocks: half, half+2, ...
-        if (half) { y0b = 32; while (y0b >= g.rows) { y0b -= g.rows; x0b++; } col = 32; }
-        for (; col < col_limit; col += 64) {
+        // columns of this chunk some window of the warp can touch: [wc_lo, wc_hi)
+        const int wc_lo = max(0, (wx_lo - chunk_x0) * g.rows);
+        const int wc_hi = min(col_limit, (wx_hi - chunk_x0 + 1) * g.rows);
+        // this thread's blocks: half, half+2, ... restricted to that range
+        int col = (wc_lo & ~63) + half * 32;
+        if (col + 32 <= wc_lo) col += 64;
+        int x0b = chunk_x0 + col / g.rows, y0b = col - (col / g.rows) * g.rows;   // cell coords of column `col`
+        const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * kAccCols;
+        for (; col < wc_hi; col += 64) {
           const int cb = chunk_cell + col;
           // validity of the block's 32 cells (uniform), minus the padding columns
           const int o = cb - base_bit;
@@ -368,19 +433,31 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
           if (lead_end >= cb) m = (lead_end - cb >= 31) ? 0u : (m & ~((2u << (lead_end - cb)) - 1u));
           if (__any_sync(0xffffffffu, m != 0)) {
             int v[32];
-            tmem_ld_32x32(tmem_base + ((uint32_t)(qd * 32) << 16) + acc * kAccCols + col, v);
+            tmem_ld_32x32(t_row + col, v);
             tmem_ld_wait();
-            if (m != 0) {
+            // branch-free: which in-window, valid columns exceed the key filter?
+            uint32_t trig = 0;
 #pragma unroll
-              for (int j = 0; j < 32; j++) {
-                if ((m >> j) & 1u) {
-                  const int n = (int)((unsigned)v[j] * (unsigned)v[j]);
-                  const int key = n ^ flip;
-                  if (key > curmax) {
-                    curmax = key;
-                    const float s = __fdiv_rn(__int2float_rn(n), den_f);
-                    if (s > g.accept_gt && (!have || s > bs)) { have = true; bs = s; bcell = cb + j; }
-                  }
+            for (int j = 0; j < 32; j++) {
+              const int key = (int)((unsigned)v[j] * (unsigned)v[j]) ^ flip;
+              trig |= (key > curmax) ? (1u << j) : 0u;
+            }
+            trig &= m;
+            // survivors (rare): exact score, in column order, one TMEM column at a time
+            uint32_t any = __reduce_or_sync(0xffffffffu, trig);
+            while (any) {
+              const int j = __ffs(any) - 1;
+              any &= any - 1;
+              int vj;
+              tmem_ld_32x1(t_row + col + j, vj);
+              tmem_ld_wait();
+              if (trig & (1u << j)) {
+                const int n = (int)((unsigned)vj * (unsigned)vj);
+                const int key = n ^ flip;
+                if (key > curmax) {
+                  curmax = key;
+                  const float s = __fdiv_rn(__int2float_rn(n), den_f);
+                  if (s > g.accept_gt && (bcell < 0 || s > bs)) { bs = s; bcell = cb + j; }
                 }
               }
             }
@@ -395,14 +472,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 
       // ---- merge the row's two threads: larger score, ties to the earlier cell
       MergeSlot* mslot = sM + (tile & 1) * kTileQ + row;
-      if (half == 1) { mslot->s = bs; mslot->cell = have ? bcell : -1; }
+      if (half == 1) { mslot->s = bs; mslot->cell = bcell; }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       if (half == 0 && active) {
         const float os = mslot->s;
         const int oc = mslot->cell;
-        if (oc >= 0 && (!have || os > bs || (os == bs && oc < bcell))) { have = true; bs = os; bcell = oc; }
+        if (oc >= 0 && (bcell < 0 || os > bs || (os == bs && oc < bcell))) { bs = os; bcell = oc; }
         const size_t out = (size_t)pair * g.top_n + t.q0 + row;
-        best_cell[out] = have ? bcell : -1;
+        best_cell[out] = bcell;
         best_score[out] = bs;
       }
       __syncwarp();
@@ -471,7 +548,8 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
     MV_CHECK_LAUNCH(ctx);
   }
   const size_t smem = 1024 + (size_t)kBStages * kBStageBytes + (size_t)kAStages * kAStageBytes +
-                      sizeof(uint32_t) * (size_t)kAStages * g.vwords + sizeof(MergeSlot) * 2 * kTileQ;
+                      sizeof(uint32_t) * (size_t)kAStages * ((g.vwords + 3) & ~3) +
+                      sizeof(RowInfo) * kAStages * kTileQ + sizeof(MergeSlot) * 2 * kTileQ;
   if (smem > 227 * 1024) MV_BAD_ARG(ctx, "tensor-core matcher: grid too large for the shared-memory validity window");
   MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;

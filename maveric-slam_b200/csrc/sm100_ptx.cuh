@@ -108,6 +108,11 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, int (&v)[32]) {
       : "memory");
 }
 
+// one column: thread l receives lane (base_lane + l), column col
+__device__ __forceinline__ void tmem_ld_32x1(uint32_t taddr, int& v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+
 // ------------------------------------------------------------------ UMMA descriptors
 // K-major operand, 64-byte rows, SWIZZLE_64B: 8 rows form a 512-byte atom in which the 16-byte
 // chunk index is XORed with (row>>1)&3 -- what a TMA box with a 64-byte inner extent and
