@@ -40,7 +40,8 @@ N_FRAMES = 4541
 TOP_N, MAX_VALID, MAX_MATCHES = 1000, 8192, 1024
 HYPOTHESES, SAMPLE_ITERS, REFINE_ITERS = 1024, 4, 10
 SEED = 0
-FLOPS_PER_POINT = 125      # FP32 flops of one correspondence in one GN pass
+FLOPS_NORMAL = 127         # FP32 flops of one correspondence in one Gauss-Newton pass (FMA = 2)
+FLOPS_SCORE = 32           # ... in the final scoring pass (residual, gate, cost: no normal equations)
 WORKLOAD = ("KITTI-00-length synthetic sequence: 4541 frames (4540 pairs), 47x155 cells, ~1k keypoints/frame, "
             "r=4 window match + RANSAC-E + GN-PnP 1024 hyp x (4+10) iters")
 
@@ -169,9 +170,13 @@ def main():
     ap.add_argument("--frames", type=int, default=N_FRAMES, help="sequence length (default: KITTI-00, 4541)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--tensor-cores", action="store_true", help="use the tcgen05 matcher")
-    ap.add_argument("--lanes", type=int, default=1, help="threads cooperating on one PnP hypothesis")
+    ap.add_argument("--matcher", default="tcgen05", choices=["tcgen05", "dp4a"],
+                    help="windowed matcher: tcgen05 tile GEMM (default) or the dp4a warp-per-query kernel")
+    ap.add_argument("--tensor-cores", action="store_true", help="same as --matcher tcgen05")
+    ap.add_argument("--lanes", type=int, default=1,
+                    help="PnP summation lanes per hypothesis (1: one thread; 2: one thread, packed FFMA2; 4..32: threads)")
     args = ap.parse_args()
+    args.tensor_cores = args.tensor_cores or args.matcher == "tcgen05"
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -261,7 +266,8 @@ def main():
     cells = ROWS * COLS
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_nominal = sm_count * 128 * 2 * sm_max * 1e6 / 1e12   # TFLOP/s, FMA = 2 flops
-    pnp_flops = (count * HYPOTHESES * SAMPLE_ITERS * 8 + HYPOTHESES * (REFINE_ITERS + 1) * n_corr) * FLOPS_PER_POINT
+    pnp_flops = (count * HYPOTHESES * SAMPLE_ITERS * 8 * FLOPS_NORMAL
+                 + HYPOTHESES * n_corr * (REFINE_ITERS * FLOPS_NORMAL + FLOPS_SCORE))
     pnp_bytes = 20 * n_corr + 64 * count
     pnp_ms = prof["pnp"]
 
@@ -272,17 +278,56 @@ def main():
                 "frac": ach / hbm_peak if ach else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_,
                 "peak_source": peak_src}
 
-    n_q = int(min(TOP_N, 1e9)) * count
+    # ---- matcher work: algorithmic int8 ops (2*256*sum_q |window_q|, cells valid or
+    # not) and, for the tensor-core matcher, the tile ops the tensor pipe executes (untimed pass)
+    idx_t, prob_t, _ = tr.softmax(semi, scale)
+    qp_t, _, _, qc_t, _ = tr.top_n(idx_t, prob_t, TOP_N, MAX_VALID)
+    qp_h, qc_h = qp_t.cpu().numpy(), qc_t.cpu().numpy()
+    del idx_t, prob_t, qp_t, qc_t
+    win_cells = 0
+    tile_ops = 0
+    cx = max(1, min(256 // ROWS, COLS))
+    n_chunk = (cx * ROWS + 15) // 16 * 16
+    for f in range(1, my_frames):
+        pq = qp_h[f, :min(int(qc_h[f]), TOP_N)].astype(np.int64)
+        if pq.size == 0:
+            continue
+        x, y = pq // ROWS, pq % ROWS
+        w = np.clip(np.minimum(x + 4 + 4, COLS - 1) - np.maximum(x + 4 - 4, 0) + 1, 0, None)
+        h = np.clip(np.minimum(y + 4 + 4, ROWS - 1) - np.maximum(y + 4 - 4, 0) + 1, 0, None)
+        win_cells += int((w * h).sum())
+        for q0 in range(0, pq.size, 128):
+            xt = x[q0:q0 + 128]
+            X0, X1 = max(int(xt.min()) + 4 - 4, 0), min(int(xt.max()) + 4 + 4, COLS - 1)
+            if X1 >= X0:
+                tile_ops += ((X1 - X0 + cx) // cx) * 2 * 128 * n_chunk * 64
+    match_alg_ops = 2 * 256 * win_cells
+    int8_peak = 2.0 * (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)
+                       if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0)
+    match_ms = prof["match"]
+    if args.tensor_cores:
+        match_entry = {"kernel": "match_tc_kernel (K1, tcgen05 kind::i8 + TMA)", "bound": "tensor",
+                       "achieved": tile_ops / (match_ms * 1e-3) / 1e12 if match_ms else None, "peak": int8_peak,
+                       "unit": "TOP/s", "frac": (tile_ops / (match_ms * 1e-3) / 1e12) / int8_peak if match_ms else None,
+                       "ms_per_launch": match_ms, "executed_tile_int8_ops": tile_ops, "algorithmic_int8_ops": match_alg_ops,
+                       "algorithmic_TOPs": match_alg_ops / (match_ms * 1e-3) / 1e12 if match_ms else None,
+                       "peak_source": "2 x measured dense bf16 (MEASURED_PEAKS.json); int8 dense peak not measured by the driver",
+                       "note": "K=64 per tile (the reference scores 64 dims) and an exact-score epilogue: epilogue-bound, "
+                               "see DESIGN.md 4.1 and profiles/"}
+    else:
+        match_entry = None
     rooflines = [
-        {"kernel": "pnp_gn_kernel<1> (K3)", "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
+        {"kernel": "pnp_gn_kernel<%d> (K3)" % args.lanes, "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
          "peak": fp32_nominal, "unit": "TFLOP/s",
          "frac": (pnp_flops / (pnp_ms * 1e-3) / 1e12) / fp32_nominal if pnp_ms else None,
          "ms_per_launch": pnp_ms, "algorithmic_flops": pnp_flops,
-         "peak_source": "nominal: SMs x 128 FMA/clk x 2 x clocks.max.sm from MEASURED_PEAKS.json",
+         "peak_source": "nominal: SMs x 128 FMA/clk x 2 x clocks.max.sm from MEASURED_PEAKS.json "
+                        "(FFMA microbenchmark on this pool: 72.9 TFLOP/s, profiles/r01/ffma_peak.txt)",
          "hbm_achieved_gbs": pnp_bytes / (pnp_ms * 1e-3) / 1e9 if pnp_ms else None},
         hbm_entry("softmax_cells_kernel (K0a)", "detect", my_frames * cells * (65 + 8)),
         hbm_entry("top_n_kernel (K0b)", "topn", my_frames * (cells * 8 * 2 + TOP_N * 12)),
-        hbm_entry("match_queries_kernel (K1a)", "match",
+        match_entry if match_entry else
+        hbm_entry("match_queries_kernel (K1a, dp4a)", "match",
                   count * (256 * (TOP_N + int(0.14 * cells) * 2) + 8 * cells + 8 * TOP_N)),
     ]
     step_kernel_ms = sum(v for v in prof.values())
@@ -343,6 +388,7 @@ def main():
             "config": {"workload": WORKLOAD, "frames": n_frames, "pairs": n_pairs, "grid": [ROWS, COLS],
                        "top_n": TOP_N, "max_matches": MAX_MATCHES, "hypotheses": HYPOTHESES,
                        "gn_iters": [SAMPLE_ITERS, REFINE_ITERS], "pnp_lanes_per_hypothesis": args.lanes, "matcher": "tcgen05" if args.tensor_cores else "dp4a",
+                       "match_algorithmic_int8_ops_per_step": match_alg_ops,
                        "sharding": f"{world} x contiguous pair blocks, all_gather of 64 B/pair",
                        "cache": f"inputs {in_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
                        "mean_matches_per_pair": n_corr / max(1, count)},

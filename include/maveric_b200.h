@@ -92,7 +92,8 @@ typedef struct {
   int max_matches;         /* MAX_NUM_MATCH (150 in the reference) */
   double match_threshold;  /* MATCH_THRESHOLD (0.9); compared squared, in double */
   double min_prob0;        /* candidate gate, 0.2 at tracking_main.c:146 */
-  int use_tensor_cores;    /* 0: dp4a warp-per-query kernel, 1: tcgen05 tile kernel */
+  int use_tensor_cores;    /* 0: dp4a warp-per-query kernel, 1: tcgen05 tile kernel, 2 (default): tcgen05
+                            * where its limits hold (rows <= 256), else dp4a.  Same results either way. */
 } mv_match_params;
 
 void mv_match_params_default(mv_match_params* p, int rows, int cols);

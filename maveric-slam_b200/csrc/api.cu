@@ -601,7 +601,10 @@ static mv_status seq_detect(mv_ctx* c, const mv_track_params* p, int n_frames, c
 }
 
 #include <functional>
-static std::function<void(const char*)> g_seq_mark;  // MV_HOST_TRACE debug hook
+static thread_local std::function<void(const char*)> g_seq_mark;  // MV_HOST_TRACE debug hook
+// Host-pipelined path: called right after the matcher has been enqueued, before the pose
+// kernels -- the point where the next chunk's row gather is released (see below).
+static thread_local std::function<mv_status()> g_after_match;
 
 // Match + pose half: needs descriptors (only rows of candidate / query cells are read) and
 // depth (only at matched frame-0 cells).
@@ -615,6 +618,7 @@ static mv_status seq_match_pose(mv_ctx* c, const mv_track_params* p, int n_frame
   if ((st = mv_match_batch(c, &p->match, n_frames, n_pairs, N, nullptr, nullptr, d_desc, w.idx, w.prob, w.qp, w.qi,
                            w.qc, w.mp, w.mc, w.mcell, nullptr, nullptr)))
     return st;
+  if (g_after_match && (st = g_after_match())) return st;
   if (p->ransac_iterations > 0) {
     if ((st = mv_ransac_identity_batch(c, n_pairs, M, w.mp, w.mc, p->ransac_iterations, p->ransac_threshold,
                                        w.rin, nullptr, nullptr)))
@@ -709,6 +713,13 @@ gather_rows_kernel(long long total_cells, const uint8_t* __restrict__ flags, con
   if (lane == 0 && moved) atomicAdd(rows_moved, moved);
 }
 
+struct PnpResidencyCap {  // cap the PnP kernel's CTAs per SM for a scope
+  mv_ctx* c;
+  int saved;
+  PnpResidencyCap(mv_ctx* ctx, int cap) : c(ctx), saved(ctx->pnp_max_ctas_per_sm) { ctx->pnp_max_ctas_per_sm = cap; }
+  ~PnpResidencyCap() { c->pnp_max_ctas_per_sm = saved; }
+};
+
 struct StreamSwap {  // run the context's kernels on another stream for a scope
   mv_ctx* c;
   cudaStream_t saved;
@@ -760,6 +771,10 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     }
   }
 
+  // The PnP kernel (64 registers x 128 threads) would otherwise take 8 CTAs = the whole register
+  // file of an SM and starve the one-warp row-gather kernel that must run beside it.
+  PnpResidencyCap residency(c, 7);
+
   constexpr int NB = 3;  // chunks in flight: staging DMA / row gather / compute
   void *bs[NB], *bd[NB], *bz[NB], *bsc[NB], *dres, *dmoved;
   SeqScratch w[NB];
@@ -786,9 +801,9 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   //   copy_stream    DMA of a chunk's logits (and descriptors/depth when not gathering)
   //   stream         in order: detector + row marking of chunk k+1, then match + pose of chunk k
   //   gather_stream  zero-copy pull of chunk k+1's marked descriptor rows, concurrent with the
-  //                  PnP launch of chunk k.  That launch fills the SMs (7 CTAs x 128 threads x 72
-  //                  registers = all but 1024 registers per SM); the gather kernel is a one-warp,
-  //                  32-register CTA, i.e. exactly the remainder, so it is resident alongside.
+  //                  PnP launch of chunk k.  That launch is capped at 7 CTAs per SM (above), which
+  //                  leaves a register slice free; the gather kernel is a one-warp, 32-register
+  //                  CTA that fits in it, so it is resident alongside.
   // whatever the caller queued on the compute stream must be ordered before the staging
   cudaEvent_t start;
   MV_CUDA(c, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
@@ -838,6 +853,36 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     mark("dma_end", k, cs);
     return MV_OK;
   };
+  // The row gather of chunk k+1 runs beside the pose kernels of chunk k, not beside its matcher:
+  // the tensor-core matcher is one latency-sensitive CTA per SM, and zero-copy host reads
+  // queued on the same SM stretch its global loads; the pose kernel (FP32-bound, its inputs in
+  // shared memory) does not care.
+  int pending_gather = -1;
+  cudaEvent_t matched;
+  MV_CUDA(c, cudaEventCreateWithFlags(&matched, cudaEventDisableTiming));
+  auto launch_gather = [&](int k, cudaEvent_t after) -> mv_status {
+    const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
+    cudaStream_t gs = c->gather_stream;
+    MV_CUDA(c, cudaStreamWaitEvent(gs, detected[b], 0));
+    if (after) MV_CUDA(c, cudaStreamWaitEvent(gs, after, 0));
+    mark("gat_beg", k, gs);
+    // An SM's L1/shared split is per-SM state: a kernel that asks for no shared memory
+    // configures "all L1", and the PnP CTAs (7 x 31 KB shared) then cannot join that SM until
+    // it drains.  Ask for the max-shared carveout so both kernels agree on the split.
+    static bool carveout_set = false;
+    if (!carveout_set) {
+      cudaFuncSetAttribute(gather_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+      carveout_set = true;
+    }
+    gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>(
+        (long long)nf * cells, w[b].flags, hd_desc + (size_t)p0 * cells * 256, hd_depth + (size_t)p0 * cells,
+        (int8_t*)bd[b], (float*)bz[b], (unsigned long long*)dmoved);
+    MV_CHECK_LAUNCH(c);
+    MV_CUDA(c, cudaEventRecord(ready[b], gs));
+    mark("gat_end", k, gs);
+    return MV_OK;
+  };
   auto stage_detect = [&](int k) -> mv_status {
     const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
     mv_status s2;
@@ -853,27 +898,12 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     }
     MV_CUDA(c, cudaEventRecord(detected[b], c->stream));
     mark("det_end", k, c->stream);
-    if (gather) {
-      cudaStream_t gs = c->gather_stream;
-      MV_CUDA(c, cudaStreamWaitEvent(gs, detected[b], 0));
-      mark("gat_beg", k, gs);
-      // An SM's L1/shared split is per-SM state: a kernel that asks for no shared memory
-      // configures "all L1", and the PnP CTAs (7 x 21 KB shared) then cannot join that SM until
-      // it drains.  Ask for the max-shared carveout so both kernels agree on the split.
-      static bool carveout_set = false;
-      if (!carveout_set) {
-        cudaFuncSetAttribute(gather_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        carveout_set = true;
-      }
-      gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>(
-          (long long)nf * cells, w[b].flags, hd_desc + (size_t)p0 * cells * 256, hd_depth + (size_t)p0 * cells,
-          (int8_t*)bd[b], (float*)bz[b], (unsigned long long*)dmoved);
-      MV_CHECK_LAUNCH(c);
-      MV_CUDA(c, cudaEventRecord(ready[b], gs));
-      mark("gat_end", k, gs);
-    } else {
+    if (!gather) {
       MV_CUDA(c, cudaEventRecord(ready[b], c->stream));
+    } else if (k == 0) {
+      return launch_gather(0, nullptr);
+    } else {
+      pending_gather = k;   // released by chunk k-1's matcher, see stage_compute
     }
     return MV_OK;
   };
@@ -883,10 +913,17 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     MV_CUDA(c, cudaStreamWaitEvent(c->stream, ready[b], 0));
     mark("cmp_beg", k, c->stream);
     if (trace) g_seq_mark = [&, k](const char* what) { mark(what, k, c->stream); };
-    if ((s2 = seq_match_pose(c, p, nf, (const int8_t*)bd[b], (const float*)bz[b], w[b],
-                             (mv_pair_result*)dres + p0, p0)))
-      return s2;
+    g_after_match = [&, k]() -> mv_status {
+      mark("match_end", k, c->stream);
+      if (pending_gather != k + 1) return MV_OK;
+      pending_gather = -1;
+      MV_CUDA(c, cudaEventRecord(matched, c->stream));
+      return launch_gather(k + 1, matched);
+    };
+    s2 = seq_match_pose(c, p, nf, (const int8_t*)bd[b], (const float*)bz[b], w[b], (mv_pair_result*)dres + p0, p0);
+    g_after_match = nullptr;
     g_seq_mark = nullptr;
+    if (s2) return s2;
     MV_CUDA(c, cudaEventRecord(consumed[b], c->stream));
     mark("cmp_end", k, c->stream);
     return MV_OK;
@@ -911,6 +948,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     cudaEventDestroy(ready[i]); cudaEventDestroy(consumed[i]); cudaEventDestroy(detected[i]); cudaEventDestroy(copied[i]);
   }
   cudaEventDestroy(start);
+  cudaEventDestroy(matched);
   if (trace) {
     for (auto& m : marks) {
       float ms = 0.f;

@@ -229,7 +229,7 @@ extern "C" void mv_match_params_default(mv_match_params* p, int rows, int cols) 
   p->max_matches = 150;                            // :13
   p->match_threshold = 0.9;                        // :12
   p->min_prob0 = 0.2;                              // :146
-  p->use_tensor_cores = 0;
+  p->use_tensor_cores = 2;                         // auto: tcgen05 tile kernel where its shape limits hold
 }
 
 mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs, int top_n,
@@ -257,7 +257,12 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
   st = mv_scratch(ctx, "match.best_score", sizeof(float) * (size_t)n_pairs * top_n, &bsc);
   if (st) return st;
 
-  if (p->use_tensor_cores) {
+  // 0: dp4a warp-per-query kernel; 1: tcgen05 tile kernel (error if the shape is outside its
+  // limits); 2: the tcgen05 kernel when rows <= 256 and the threshold is a number, else dp4a.
+  // Both produce the same bytes (tests/test_gpu_parity.py); tools/match_sweep.py times them.
+  int use_tc = p->use_tensor_cores;
+  if (use_tc == 2) use_tc = (p->rows <= 256 && n_frames > 0 && p->match_threshold * p->match_threshold >= 0.0) ? 1 : 0;
+  if (use_tc) {
     st = mv_match_tc_launch(ctx, p, n_frames, n_pairs, top_n, d_f0, d_f1, d_desc, d_max_idx, d_prob,
                             d_q_patch, d_q_count, (int32_t*)bc, (float*)bsc);
     if (st) return st;

@@ -206,7 +206,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       if (lane == 0) {
         for (int c = 0; c < t.n_chunks; c++, chunk++) {
           const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
-          mbar_wait(smem_u32(&bar_empty_b[s]), ph ^ 1, abort_flag, 1);
+          mbar_wait(smem_u32(&bar_empty_b[s]), ph ^ 1, abort_flag, 1, 256);
           mbar_expect_tx(smem_u32(&bar_full_b[s]), box_bytes);
           tma_load_4d(smem_u32(sB + s * kBStageBytes), &tmap, smem_u32(&bar_full_b[s]), 0, 0, t.X0 + c * g.cx, t.f0);
         }
@@ -222,12 +222,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       if (t.n_rows == 0) continue;
       if (lane == 0) {
         const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
-        mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 2);
+        mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 2, 128);
         const uint32_t a_addr = smem_u32(sA + a * kAStageBytes);
         for (int c = 0; c < t.n_chunks; c++, chunk++) {
           const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
           const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
-          mbar_wait(smem_u32(&bar_acc_empty[acc]), accph ^ 1, abort_flag, 3);
+          mbar_wait(smem_u32(&bar_acc_empty[acc]), accph ^ 1, abort_flag, 3, 64);
           mbar_wait(smem_u32(&bar_full_b[s]), ph, abort_flag, 4);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(sB + s * kBStageBytes);
@@ -251,7 +251,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
       if (t.n_rows == 0) continue;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
-      mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5);
+      mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5, 512);
 
       // validity words of the tile's cell range (plus the overrun of the last chunk)
       const int w_lo = (t.X0 * g.rows) >> 5;
@@ -436,11 +436,16 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
             tmem_ld_32x32(t_row + col, v);
             tmem_ld_wait();
             // branch-free: which in-window, valid columns exceed the key filter?
+            // key > curmax  <=>  n > curmax (flip = 0)  /  n < ~curmax (flip = -1); the flipped
+            // lanes test n <= ~curmax, a superset the exact path re-checks: one compare with the
+            // lane's flip folded in as a predicate, no per-column xor.
+            const bool flipb = flip != 0;
+            const int cm = flipb ? ~curmax : curmax;
             uint32_t trig = 0;
 #pragma unroll
             for (int j = 0; j < 32; j++) {
-              const int key = (int)((unsigned)v[j] * (unsigned)v[j]) ^ flip;
-              trig |= (key > curmax) ? (1u << j) : 0u;
+              const int n = (int)((unsigned)v[j] * (unsigned)v[j]);
+              trig |= ((n > cm) != flipb) ? (1u << j) : 0u;
             }
             trig &= m;
             // survivors (rare): exact score, in column order, one TMEM column at a time

@@ -46,10 +46,14 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int who) {
+// `backoff_ns` > 0: sleep between probes -- for producer-side waits (a free slot), which are long
+// and off the critical path; a spinning warp would otherwise take issue slots from the epilogue.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int who,
+                                          unsigned backoff_ns = 0) {
   uint64_t t0 = 0;
   for (uint32_t i = 1;; i++) {
     if (mbar_try_wait(bar, parity)) return;
+    if (backoff_ns) __nanosleep(backoff_ns);
     if ((i & 255u) == 0) {
       const uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;

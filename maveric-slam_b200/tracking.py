@@ -100,12 +100,13 @@ def compute_top_N(scale, semi, N, max_valid: int = 1000, ctx: _lib.Context | Non
 
 
 def match_params(rows, cols, shift_x=4, shift_y=4, radius=4, max_matches=150, match_threshold=0.9,
-                 min_prob0=0.2, use_tensor_cores=False) -> _lib.MatchParams:
+                 min_prob0=0.2, use_tensor_cores=None) -> _lib.MatchParams:
     p = _lib.MatchParams()
     _lib.load().mv_match_params_default(C.byref(p), rows, cols)
     p.shift_x, p.shift_y, p.radius, p.max_matches = shift_x, shift_y, radius, max_matches
     p.match_threshold, p.min_prob0 = match_threshold, min_prob0
-    p.use_tensor_cores = 1 if use_tensor_cores else 0
+    if use_tensor_cores is not None:      # None keeps the library default (2 = auto)
+        p.use_tensor_cores = 1 if use_tensor_cores else 0
     return p
 
 
@@ -194,13 +195,14 @@ def track(last_frame: Frame | None, current_frame: Frame, x_shift=4, y_shift=4, 
 # --------------------------------------------------------------------------------------
 def track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=1024, radius=4,
                  shift=(4, 4), refine_iters=10, sample_iters=4, ransac_iterations=10, lanes=1, seed=0,
-                 use_tensor_cores=False, first_pair=0) -> _lib.TrackParams:
+                 use_tensor_cores=None, first_pair=0) -> _lib.TrackParams:
     p = _lib.TrackParams()
     _lib.load().mv_track_params_default(C.byref(p), rows, cols)
     p.top_n, p.max_valid = top_n, max_valid
     p.match.max_matches, p.match.radius = max_matches, radius
     p.match.shift_x, p.match.shift_y = shift
-    p.match.use_tensor_cores = 1 if use_tensor_cores else 0
+    if use_tensor_cores is not None:
+        p.match.use_tensor_cores = 1 if use_tensor_cores else 0
     p.pnp.hypotheses, p.pnp.refine_iters, p.pnp.sample_iters = hypotheses, refine_iters, sample_iters
     p.pnp.lanes_per_hypothesis, p.pnp.seed, p.pnp.first_pair = lanes, seed, first_pair
     p.ransac_iterations = ransac_iterations
