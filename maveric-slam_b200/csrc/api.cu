@@ -6,6 +6,7 @@
 // point needs a CUDA device and reports MV_ERR_NO_DEVICE (new API) or aborts with a
 // message on stderr (legacy void symbols) when there is none.
 #include "mv_common.cuh"
+#include "sm100_ptx.cuh"
 #include "svd3.cuh"
 
 #include <math.h>
@@ -675,41 +676,88 @@ __global__ void mark_query_rows_kernel(int cells, int top_n, const int32_t* __re
     flags[(size_t)f * cells + q_patch[(size_t)f * top_n + i]] |= 2;
 }
 
-__global__ void __maxnreg__(32)
+// One warp per SM.  Rows move host -> shared -> device through the TMA unit (cp.async.bulk ->
+// UBLKCP): flagged cells are queued 32 at a time, each lane issues the 256-byte bulk load of one
+// row into a shared-memory slot (completion on an mbarrier) and, one stage later, the bulk
+// store of that slot to the device row.  Nothing passes through the SM's load/store pipeline,
+// whose in-order return queue would otherwise hold every device load of the co-resident
+// kernels behind multi-microsecond PCIe reads (measured: the tensor-core matcher ran 12x
+// slower beside an LDG-based gather).  Two 8 KB stages keep ~2.4 MB in flight chip-wide.
+constexpr int kGatherStages = 2;
+__global__ void __launch_bounds__(32)
 gather_rows_kernel(long long total_cells, const uint8_t* __restrict__ flags, const int8_t* __restrict__ h_desc,
-                   const float* __restrict__ h_depth, int8_t* __restrict__ d_desc, float* __restrict__ d_depth,
-                   unsigned long long* __restrict__ rows_moved) {
-  const int lane = threadIdx.x & 31;
-  const int half = lane >> 4, l16 = lane & 15;  // 16 lanes x 16 B = one 256-byte row
-  const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+                   int8_t* __restrict__ d_desc, unsigned long long* __restrict__ rows_moved) {
+  __shared__ __align__(128) uint8_t slots[kGatherStages][32][256];
+  __shared__ uint64_t bar[kGatherStages];
+  __shared__ long long queue[64];
+  const int lane = threadIdx.x;
+  if (lane == 0) {
+    for (int i = 0; i < kGatherStages; i++) sm100::mbar_init(sm100::smem_u32(&bar[i]), 1);
+    sm100::mbar_fence_init();
+  }
+  __syncwarp();
   const long long groups = (total_cells + 31) >> 5;
+  int queued = 0;                    // flagged cells waiting in queue[]
   unsigned long long moved = 0;
-  for (long long g = warp; g < groups; g += n_warps) {
+  int stage = 0;
+  unsigned used[kGatherStages] = {0, 0};   // times each stage's barrier has been armed
+  long long pend_cell = -1;          // this lane's row in the stage whose load is in flight
+  int pend_stage = -1;
+
+  auto flush_pending = [&]() {       // wait for the in-flight stage, then store its rows
+    if (pend_stage < 0) return;
+    sm100::mbar_wait(sm100::smem_u32(&bar[pend_stage]), (used[pend_stage] - 1) & 1, nullptr, 9);
+    if (pend_cell >= 0)
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;"
+                   ::"l"(reinterpret_cast<uint64_t>(d_desc + pend_cell * 256)),
+                     "r"(sm100::smem_u32(&slots[pend_stage][lane][0]))
+                   : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    pend_stage = -1;
+    pend_cell = -1;
+  };
+  auto issue = [&](int n) {          // load the first n (<= 32) queued rows into `stage`
+    // the store that last read this stage's slots (the most recent bulk group) must have
+    // finished reading them; the other stage's PCIe load stays in flight meanwhile
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) sm100::mbar_expect_tx(sm100::smem_u32(&bar[stage]), (uint32_t)n * 256u);
+    __syncwarp();
+    const long long cell = lane < n ? queue[lane] : -1;
+    if (cell >= 0) {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], 256, [%2];"
+                   ::"r"(sm100::smem_u32(&slots[stage][lane][0])),
+                     "l"(reinterpret_cast<uint64_t>(h_desc + cell * 256)), "r"(sm100::smem_u32(&bar[stage]))
+                   : "memory");
+    }
+    used[stage]++;
+    const int this_stage = stage;
+    stage ^= 1;
+    flush_pending();                 // the other stage: its load overlapped this issue
+    pend_stage = this_stage;
+    pend_cell = cell;
+    // shift the queue
+    __syncwarp();
+    const long long rest = (lane + n < queued) ? queue[lane + n] : -1;
+    __syncwarp();
+    if (lane + n < queued) queue[lane] = rest;
+    queued -= n;
+    moved += n;
+    __syncwarp();
+  };
+
+  for (long long g = blockIdx.x; g < groups; g += gridDim.x) {
     const long long cell = (g << 5) + lane;
     const int flag = cell < total_cells ? flags[cell] : 0;
-    if (flag & 1) d_depth[cell] = h_depth[cell];
-    unsigned todo = __ballot_sync(0xffffffffu, flag != 0);
-    moved += __popc(todo);
-    while (todo) {
-      // up to six 256-byte rows in flight per warp: three loads, two rows per load
-      int r[3];
-      int4 v[3];
-#pragma unroll
-      for (int k = 0; k < 3; k++) {
-        int r0 = -1, r1 = -1;
-        if (todo) { r0 = __ffs(todo) - 1; todo &= todo - 1; }
-        if (todo) { r1 = __ffs(todo) - 1; todo &= todo - 1; }
-        r[k] = half ? r1 : r0;
-      }
-#pragma unroll
-      for (int k = 0; k < 3; k++)
-        if (r[k] >= 0) v[k] = __ldcs(reinterpret_cast<const int4*>(h_desc + ((g << 5) + r[k]) * 256) + l16);
-#pragma unroll
-      for (int k = 0; k < 3; k++)
-        if (r[k] >= 0) reinterpret_cast<int4*>(d_desc + ((g << 5) + r[k]) * 256)[l16] = v[k];
-    }
+    const unsigned votes = __ballot_sync(0xffffffffu, flag != 0);
+    if (flag) queue[queued + __popc(votes & ((1u << lane) - 1))] = cell;
+    queued += __popc(votes);
+    __syncwarp();
+    if (queued >= 32) issue(32);
   }
+  if (queued > 0) issue(queued);
+  flush_pending();
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   if (lane == 0 && moved) atomicAdd(rows_moved, moved);
 }
 
@@ -757,14 +805,11 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   bool gather = true;
   if (const char* e = getenv("MV_HOST_GATHER")) gather = atoi(e) != 0;
   const int8_t* hd_desc = nullptr;
-  const float* hd_depth = nullptr;
   if (gather) {
-    cudaPointerAttributes a1, a2;
-    if (cudaPointerGetAttributes(&a1, h_desc) == cudaSuccess && a1.type == cudaMemoryTypeHost &&
-        cudaPointerGetAttributes(&a2, h_depth) == cudaSuccess && a2.type == cudaMemoryTypeHost &&
-        a1.devicePointer && a2.devicePointer) {
+    cudaPointerAttributes a1;
+    if (cudaPointerGetAttributes(&a1, h_desc) == cudaSuccess && a1.type == cudaMemoryTypeHost && a1.devicePointer &&
+        (reinterpret_cast<uintptr_t>(a1.devicePointer) & 15) == 0) {
       hd_desc = (const int8_t*)a1.devicePointer;
-      hd_depth = (const float*)a2.devicePointer;
     } else {
       cudaGetLastError();
       gather = false;  // pageable memory: plain staged copies
@@ -841,13 +886,13 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     MV_CUDA(c, cudaMemcpyAsync(bs[b], h_semi + (size_t)p0 * cells * 65, (size_t)nf * cells * 65,
                                cudaMemcpyHostToDevice, cs));
     MV_CUDA(c, cudaMemcpyAsync(bsc[b], h_semi_scale + p0, sizeof(float) * (size_t)nf, cudaMemcpyHostToDevice, cs));
-    up += (unsigned long long)nf * ((size_t)cells * 65 + 4);
+    MV_CUDA(c, cudaMemcpyAsync(bz[b], h_depth + (size_t)p0 * cells, sizeof(float) * (size_t)nf * cells,
+                               cudaMemcpyHostToDevice, cs));
+    up += (unsigned long long)nf * ((size_t)cells * (65 + 4) + 4);
     if (!gather) {
       MV_CUDA(c, cudaMemcpyAsync(bd[b], h_desc + (size_t)p0 * cells * 256, (size_t)nf * cells * 256,
                                  cudaMemcpyHostToDevice, cs));
-      MV_CUDA(c, cudaMemcpyAsync(bz[b], h_depth + (size_t)p0 * cells, sizeof(float) * (size_t)nf * cells,
-                                 cudaMemcpyHostToDevice, cs));
-      up += (unsigned long long)nf * (size_t)cells * (256 + 4);
+      up += (unsigned long long)nf * (size_t)cells * 256;
     }
     MV_CUDA(c, cudaEventRecord(copied[b], cs));
     mark("dma_end", k, cs);
@@ -875,9 +920,9 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
                            cudaSharedmemCarveoutMaxShared);
       carveout_set = true;
     }
-    gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>(
-        (long long)nf * cells, w[b].flags, hd_desc + (size_t)p0 * cells * 256, hd_depth + (size_t)p0 * cells,
-        (int8_t*)bd[b], (float*)bz[b], (unsigned long long*)dmoved);
+    gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>((long long)nf * cells, w[b].flags,
+                                                   hd_desc + (size_t)p0 * cells * 256, (int8_t*)bd[b],
+                                                   (unsigned long long*)dmoved);
     MV_CHECK_LAUNCH(c);
     MV_CUDA(c, cudaEventRecord(ready[b], gs));
     mark("gat_end", k, gs);
@@ -957,7 +1002,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     }
     for (auto& m : marks) cudaEventDestroy(m.second);
   }
-  if (gather) up += moved * 260ull;  // 256 B descriptor row + 4 B depth per staged cell
+  if (gather) up += moved * 256ull;  // one 256 B descriptor row per staged cell
   if (h2d_bytes) *h2d_bytes = up;
   if (d2h_bytes) *d2h_bytes = sizeof(mv_pair_result) * (unsigned long long)n_pairs;
   return MV_OK;
