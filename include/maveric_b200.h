@@ -236,6 +236,38 @@ mv_status mv_track_sequence_host(mv_ctx* ctx, const mv_track_params* p, int n_fr
                                  unsigned long long* h2d_bytes, unsigned long long* d2h_bytes);
 
 /* ------------------------------------------------------------------------- */
+/* NMS between the detector and the matcher (src/run_nms.c)                     */
+/* ------------------------------------------------------------------------- */
+
+/* The 2x2-quadrant, 4-pixel non-maximum suppression of src/run_nms.c:65-156 on the per-cell
+ * detector output of every frame, in place: a suppressed cell gets max_idx = 64 and
+ * prob = 64.0f (:138-139).  The reference walks the cell corners sequentially (x outer, y
+ * inner) and later corners see earlier suppressions; the kernel keeps exactly that order with a
+ * wavefront over t = 2x + y (corners of one wavefront never share a cell), one warp per frame.
+ *   d_max_idx int32 [n_frames][rows*cols]   d_prob float [n_frames][rows*cols] */
+mv_status mv_nms_batch(mv_ctx* ctx, int n_frames, int rows, int cols, int32_t* d_max_idx, float* d_prob);
+
+/* Host-pointer, synchronous, one frame (the arrays run_nms.c's main() keeps on its stack). */
+mv_status run_nms_ex(mv_ctx* ctx, int rows, int cols, int* max_indices, float* probs);
+
+/* ------------------------------------------------------------------------- */
+/* Trajectory: chaining the pairwise poses (python/compute_trajectory.py)        */
+/* ------------------------------------------------------------------------- */
+
+/* The step after the pose gather.  The reference chains 3x4 [R|t] relative transforms
+ * (float64, row-major, transform_XXXXXX_YYYYYY.npy) into frame poses with
+ *     R_cur <- R_t R_cur,   t_cur <- t_t + t_cur        (compute_trajectory.py:76-77)
+ * starting from the identity (:51).  mv_chain_transforms does the same for n transforms as a
+ * parallel scan in float64: d_traj receives n+1 poses [R|t], pose 0 = identity.  The scan
+ * regroups the products, so poses agree with the sequential reference to ~1e-13, not bit for bit.
+ *   d_transforms double [n][12]      d_traj double [n+1][12] */
+mv_status mv_chain_transforms(mv_ctx* ctx, int n, const double* d_transforms, double* d_traj);
+
+/* The hot path's result records (unit quaternion + translation, float) as 3x4 float64
+ * transforms, the reference's interchange format (python/pairwise_pnp.py:690-694). */
+mv_status mv_results_to_transforms(mv_ctx* ctx, int n, const mv_pair_result* d_results, double* d_transforms);
+
+/* ------------------------------------------------------------------------- */
 /* Synthetic KITTI-shaped frames (counter-based, identical to oracle/ and numpy) */
 /* ------------------------------------------------------------------------- */
 typedef struct {

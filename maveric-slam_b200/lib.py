@@ -22,7 +22,7 @@ NEW_SYMBOLS = [
     "compute_softmax_ex", "compute_top_N_ex", "mv_match_params_default", "mv_match_batch",
     "mv_match_pair_host", "mv_ransac_identity_batch", "mv_pnp_params_default", "mv_pnp_gn_batch",
     "mv_build_corr_batch", "mv_track_params_default", "mv_track_sequence", "mv_track_sequence_host",
-    "mv_synth_frames",
+    "mv_chain_transforms", "mv_results_to_transforms", "mv_nms_batch", "run_nms_ex", "mv_synth_frames",
 ]
 LEGACY_SYMBOLS = [
     "add_Vector2f", "add_Vector3f", "mult_Quaternionf", "create_Quaternionf", "Quaternionf_from_Vector3f",
@@ -120,6 +120,10 @@ def load() -> C.CDLL:
     L.mv_track_sequence_host.argtypes = [vp, C.POINTER(TrackParams), i32, vp, vp, vp, vp, vp,
                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.mv_synth_frames.argtypes = [vp, C.POINTER(SynthParams), i32, i32, vp, vp, vp, vp]
+    L.mv_nms_batch.argtypes = [vp, i32, i32, i32, vp, vp]
+    L.run_nms_ex.argtypes = [vp, i32, i32, vp, vp]
+    L.mv_chain_transforms.argtypes = [vp, i32, vp, vp]
+    L.mv_results_to_transforms.argtypes = [vp, i32, vp, vp]
     # legacy symbols used from Python
     L.compute_softmax.argtypes = [f32, vp, C.POINTER(i32), vp, vp]
     L.compute_softmax.restype = None

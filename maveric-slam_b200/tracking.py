@@ -99,6 +99,15 @@ def compute_top_N(scale, semi, N, max_valid: int = 1000, ctx: _lib.Context | Non
     return pa[:k].copy(), ix[:k].copy(), pr[:k].copy()
 
 
+def run_nms(rows, cols, max_indices, probs, ctx: _lib.Context | None = None):
+    """src/run_nms.c:65-156 on one frame's detector output -> (max_indices, probs) after suppression
+    (suppressed cells: index 64, prob 64.0)."""
+    ctx = ctx or default_context()
+    mi = np.ascontiguousarray(max_indices, np.int32).copy(); pr = np.ascontiguousarray(probs, np.float32).copy()
+    ctx.check(ctx.lib.run_nms_ex(ctx.h, rows, cols, _p(mi), _p(pr)))
+    return mi, pr
+
+
 def match_params(rows, cols, shift_x=4, shift_y=4, radius=4, max_matches=150, match_threshold=0.9,
                  min_prob0=0.2, use_tensor_cores=None) -> _lib.MatchParams:
     p = _lib.MatchParams()
@@ -255,6 +264,12 @@ class Tracker:
                                                  self._d(idx), self._d(prob), self._d(nv)))
         return idx, prob, nv
 
+    def nms(self, rows, cols, max_idx, prob):
+        """In-place batched NMS (src/run_nms.c:65-156) of the detector output of every frame."""
+        n = max_idx.shape[0]
+        self.ctx.check(self.lib.mv_nms_batch(self.ctx.h, n, rows, cols, self._d(max_idx), self._d(prob)))
+        return max_idx, prob
+
     def top_n(self, max_idx, prob, top_n, max_valid):
         torch = self.torch
         n, cells = max_idx.shape
@@ -342,6 +357,63 @@ class Tracker:
         self.ctx.check(self.lib.mv_track_sequence_host(self.ctx.h, C.byref(params), n, hp(semi), hp(semi_scale),
                                                        hp(desc), hp(depth), hp(out), C.byref(up), C.byref(down)))
         return out, up.value, down.value
+
+
+    def results_to_transforms(self, results):
+        """uint8 [n, 64] result records (device) -> float64 [n, 3, 4] relative transforms [R|t], the
+        reference's interchange format (python/pairwise_pnp.py:690-694)."""
+        torch = self.torch
+        n = results.shape[0]
+        T = torch.empty((n, 3, 4), dtype=torch.float64, device=self.device)
+        self.ctx.check(self.lib.mv_results_to_transforms(self.ctx.h, n, self._d(results), self._d(T)))
+        return T
+
+    def chain_transforms(self, transforms):
+        """python/compute_trajectory.py:49-51,76-77 as a parallel scan: float64 [n, 3, 4] relative
+        transforms -> float64 [n+1, 3, 4] frame poses, pose 0 the identity."""
+        torch = self.torch
+        n = transforms.shape[0]
+        traj = torch.empty((n + 1, 3, 4), dtype=torch.float64, device=self.device)
+        self.ctx.check(self.lib.mv_chain_transforms(self.ctx.h, n, self._d(transforms), self._d(traj)))
+        return traj
+
+
+# --------------------------------------------------------------------------------------
+# trajectory files, in the reference's formats (python/compute_trajectory.py)
+# --------------------------------------------------------------------------------------
+def save_pose(filename, pose) -> None:
+    """compute_trajectory.py:49-51: the 3x4 pose, '%.6f', one row per line."""
+    np.savetxt(filename, np.asarray(pose, np.float64)[:3, :], fmt="%.6f")
+
+
+def write_ply(filename, points) -> None:
+    """compute_trajectory.py:6-43: camera centres as an ASCII PLY polyline, first vertex red, last
+    black, the others blue."""
+    points = [np.asarray(p, np.float64) for p in points]
+    n = len(points)
+    colors = [[255, 0, 0]] + [[0, 0, 255]] * max(0, n - 2) + [[0, 0, 0]]
+    with open(filename, "w") as f:
+        f.write("ply\nformat ascii 1.0\n")
+        f.write(f"element vertex {n}\n")
+        f.write("property float x\nproperty float y\nproperty float z\n")
+        f.write("property uchar red\nproperty uchar green\nproperty uchar blue\n")
+        f.write(f"element edge {n - 1}\n")
+        f.write("property int vertex1\nproperty int vertex2\nend_header\n")
+        for pt, c in zip(points, colors):
+            f.write(f"{pt[0]} {pt[1]} {pt[2]} {c[0]} {c[1]} {c[2]}\n")
+        for i in range(n - 1):
+            f.write(f"{i} {i + 1}\n")
+
+
+def write_trajectory(out_dir, start_frame: int, traj) -> None:
+    """The files compute_trajectory.py's main() leaves in out_dir (:53-89): one
+    frame-XXXXXX.pose.txt per pose and trajectory_<start>_<end>.ply."""
+    import os
+    traj = np.asarray(traj, np.float64)
+    for i, pose in enumerate(traj):
+        save_pose(os.path.join(out_dir, f"frame-{start_frame + i:06d}.pose.txt"), pose)
+    end = start_frame + len(traj) - 1
+    write_ply(os.path.join(out_dir, f"trajectory_{start_frame:06d}_{end:06d}.ply"), [p[:3, 3] for p in traj])
 
 
 def results_to_numpy(t) -> np.ndarray:

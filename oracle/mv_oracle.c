@@ -410,6 +410,69 @@ void orc_svd3(const float A[3][3], float U[3][3], float S[3][3], float V[3][3]) 
 }
 
 /* ===================================================================== */
+/* NMS between detector and matcher (src/run_nms.c:65-156)                 */
+/* ===================================================================== */
+
+/* Corners of the cell grid are visited x outer / y inner, both INCLUSIVE of the far edge
+ * (:65-66).  Each corner looks at its (up to) four adjacent cells (:75-81) and takes the cell's
+ * keypoint only if it lies within 6 px of the corner on both axes (:94-97).  Then, repeatedly:
+ * the strongest remaining keypoint suppresses every other one closer than 4 px on both axes
+ * (:131-147) and retires.  The first arg-max scan ignores patch 0 (`patches[i] > 0`, :116), the
+ * second does not (:126) -- reproduced as written. */
+int orc_nms(int rows, int cols, int* max_idx, float* probs1, int* events, int max_events) {
+  int n_events = 0;
+  for (int xi = 0; xi <= cols; xi++) {
+    for (int yi = 0; yi <= rows; yi++) {
+      int nv = 0, patches[4] = {0, 0, 0, 0}, xs[4] = {0, 0, 0, 0}, ys[4] = {0, 0, 0, 0};
+      float probs[4] = {0, 0, 0, 0};
+      for (int xd = -1; xd <= 0; xd++) {
+        int xg = xi + xd;
+        if (xg < 0 || xg >= cols) continue;
+        for (int yd = -1; yd <= 0; yd++) {
+          int yg = yi + yd;
+          if (yg < 0 || yg >= rows) continue;
+          int patch = xg * rows + yg;               /* grid_to_patch, :33-35 */
+          int index = max_idx[patch];
+          if (index == 64) continue;
+          int px = index % 8, py = index / 8;       /* :37-40 */
+          if (xd == -1 && px < 2) continue;
+          if (xd == 0 && px >= 6) continue;
+          if (yd == -1 && py < 2) continue;
+          if (yd == 0 && py >= 6) continue;
+          patches[nv] = patch; probs[nv] = probs1[patch];
+          xs[nv] = xg * 8 + px; ys[nv] = yg * 8 + py;
+          nv++;
+        }
+      }
+      for (;;) {
+        float max_prob = 0; int max_index = -1;
+        for (int i = 0; i < nv; i++)
+          if (patches[i] > 0 && probs[i] > max_prob) { max_prob = probs[i]; max_index = i; }
+        if (max_index == -1) break;
+        for (int i = 0; i < nv; i++)
+          if (patches[i] >= 0 && probs[i] > max_prob) { max_prob = probs[i]; max_index = i; }
+        for (int i = 0; i < nv; i++) {
+          if (i == max_index || patches[i] < 0) continue;
+          int xdiff = abs(xs[max_index] - xs[i]), ydiff = abs(ys[max_index] - ys[i]);
+          if (xdiff < 4 && ydiff < 4) {
+            max_idx[patches[i]] = 64;
+            probs1[patches[i]] = 64;
+            if (events && n_events < max_events) {
+              events[4 * n_events] = xs[max_index]; events[4 * n_events + 1] = ys[max_index];
+              events[4 * n_events + 2] = xs[i]; events[4 * n_events + 3] = ys[i];
+            }
+            n_events++;
+            patches[i] = -1; probs[i] = -1;
+          }
+        }
+        probs[max_index] = -1; patches[max_index] = -1;
+      }
+    }
+  }
+  return n_events;
+}
+
+/* ===================================================================== */
 /* Essential-matrix RANSAC as the reference runs it (src/pnp_solver.c)    */
 /* ===================================================================== */
 

@@ -27,6 +27,11 @@
 
 /* ---- detector post-processing (src/top_N.c) ---- */
 int  orc_softmax(float scale, const int8_t* semi, int cells, int* max_idx, float* probs);
+/* src/run_nms.c:65-156: 2x2-quadrant NMS over the per-cell keypoints, in place.  A suppressed
+ * cell gets max_idx = 64 and prob = 64.0f (run_nms.c:138-139).  events (nullable,
+ * [max_events][4]) receives (x_keep, y_keep, x_suppressed, y_suppressed) per suppression in the
+ * reference's order; returns the number of suppressions. */
+int  orc_nms(int rows, int cols, int* max_idx, float* probs, int* events, int max_events);
 int  orc_top_n(float scale, const int8_t* semi, int cells, int N, int max_valid,
                int* num_selected, int* patches, int* indices, float* probs);
 

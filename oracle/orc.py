@@ -73,6 +73,8 @@ class Oracle:
         L = self.lib
         L.orc_softmax.restype = C.c_int
         L.orc_softmax.argtypes = [C.c_float, _i8p, C.c_int, _i32p, _f32p]
+        L.orc_nms.restype = C.c_int
+        L.orc_nms.argtypes = [C.c_int, C.c_int, _i32p, _f32p, C.c_void_p, C.c_int]
         L.orc_top_n.restype = C.c_int
         L.orc_top_n.argtypes = [C.c_float, _i8p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), _i32p, _i32p, _f32p]
         L.orc_match.restype = C.c_int
@@ -106,6 +108,14 @@ class Oracle:
         pr = np.zeros(cells, np.float32)
         nv = self.lib.orc_softmax(float(scale), semi, cells, idx, pr)
         return idx, pr, nv
+
+    def nms(self, rows, cols, max_idx, probs, want_events=False):
+        """src/run_nms.c:65-156 on copies of (max_idx, probs) -> (max_idx, probs, n_suppressed[, events])."""
+        mi = np.ascontiguousarray(max_idx, np.int32).copy(); pr = np.ascontiguousarray(probs, np.float32).copy()
+        cap = rows * cols
+        ev = np.zeros((cap, 4), np.int32)
+        n = self.lib.orc_nms(rows, cols, mi, pr, ev.ctypes.data, cap)
+        return (mi, pr, n, ev[:n].copy()) if want_events else (mi, pr, n)
 
     def top_n(self, scale, semi, N, max_valid=1000):
         semi = np.ascontiguousarray(semi, np.int8)
@@ -204,6 +214,8 @@ class Reference:
         L.compute_reprojection_error.argtypes = [_f32p, _f32p, _f32p]
         L.normalize_points.argtypes = [C.c_int, _f32p, _f32p, _f32p]
         L.svd.argtypes = [C.c_float] * 9 + [C.POINTER(C.c_float)] * 27
+        L.ref_run_nms.restype = C.c_int
+        L.ref_run_nms.argtypes = [_i32p, C.POINTER(C.c_int), _i32p]
         L.matmul.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, _f32p] + [C.c_size_t] * 3 + [C.c_float] * 2 + [C.c_bool] * 2
         L.matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_bool] * 2
 
@@ -229,6 +241,16 @@ class Reference:
         n = self.lib.ref_run_tracking(p1, p2, C.byref(ni), inl, E)
         return dict(n=n, pts0=p1[:n].copy(), pts1=p2[:n].copy(), num_inliers=ni.value,
                     inliers=inl[:ni.value].copy(), best_E=E)
+
+    def run_nms(self, semi_scale1, semi1):
+        """Runs the reference's run_nms main() (src/run_nms.c:42-175) on this frame (its image1).
+        Returns (suppression events [n,4], surviving keypoints [m,2] in patch order)."""
+        z = np.zeros((1920, 256), np.int8)
+        self.lib.ref_load_pair(1.0, np.zeros((1920, 65), np.int8), 1.0, z, float(semi_scale1),
+                               np.ascontiguousarray(semi1, np.int8), 1.0, z)
+        ev = np.zeros((4096, 4), np.int32); kp = np.zeros((1920, 2), np.int32); ne = C.c_int(0)
+        nk = self.lib.ref_run_nms(ev, C.byref(ne), kp)
+        return ev[:ne.value].copy(), kp[:nk].copy()
 
     def ransac(self, pts1, pts2, K, iters=10, thr=1.1):
         pts1 = np.ascontiguousarray(pts1, np.float32); pts2 = np.ascontiguousarray(pts2, np.float32)

@@ -98,6 +98,41 @@ int ref_run_tracking(float* pts1, float* pts2, int* num_inliers, int* inliers, f
   return g_num_matches;
 }
 
+/* ---- src/run_nms.c: main() renamed to ref_nms_main, its printf to ref_nms_printf, and its
+ * three helper names that clash with tracking_main.c's prefixed with nms_ (oracle/Makefile).
+ * The driver reports only through stdout: "(x y) suppressing (x y)" per suppression (:141) and
+ * "x y" per surviving keypoint (:172). */
+static int g_nms_events[4096][4], g_nms_n_events, g_nms_kp[1920][2], g_nms_n_kp;
+int ref_nms_printf(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  if (fmt[0] == '(') {
+    int a = va_arg(ap, int), b = va_arg(ap, int), c = va_arg(ap, int), d = va_arg(ap, int);
+    if (g_nms_n_events < 4096) {
+      g_nms_events[g_nms_n_events][0] = a; g_nms_events[g_nms_n_events][1] = b;
+      g_nms_events[g_nms_n_events][2] = c; g_nms_events[g_nms_n_events][3] = d;
+    }
+    g_nms_n_events++;
+  } else {
+    int a = va_arg(ap, int), b = va_arg(ap, int);
+    if (g_nms_n_kp < 1920) { g_nms_kp[g_nms_n_kp][0] = a; g_nms_kp[g_nms_n_kp][1] = b; }
+    g_nms_n_kp++;
+  }
+  va_end(ap);
+  return 0;
+}
+int ref_nms_main(void);
+/* Runs the reference's run_nms main() on image1 of the loaded pair.  events [4096][4],
+ * keypoints [1920][2]; returns the number of surviving keypoints. */
+int ref_run_nms(int* events, int* n_events, int* keypoints) {
+  g_nms_n_events = 0; g_nms_n_kp = 0;
+  ref_nms_main();
+  if (events) memcpy(events, g_nms_events, sizeof(g_nms_events));
+  if (n_events) *n_events = g_nms_n_events;
+  if (keypoints) memcpy(keypoints, g_nms_kp, sizeof(g_nms_kp));
+  return g_nms_n_kp;
+}
+
 /* The matmul shim and the local feature pool are header-only in the reference:
  * instantiate them here so tests can call the originals. */
 #include "gemmini_functions_cpu.h"

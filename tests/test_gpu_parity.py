@@ -333,3 +333,26 @@ def test_track_legacy_symbol(tk, image0, kat):
     assert np.abs(R - R1).max() < 5e-3      # R1 comes from an approximate SVD, not exactly orthonormal
     q0, t0 = tk.track(None, f)
     assert list(q0) == [1, 0, 0, 0] and list(t0) == [0, 0, 0]
+
+
+# ------------------------------------------------------------------ NMS (src/run_nms.c), SURVEY §8f rank 1
+@pytest.mark.parametrize("rows,cols,permille", [(24, 80, 140), (24, 80, 1000), (47, 155, 550), (94, 310, 700),
+                                                (5, 7, 900), (40, 3, 900)])
+def test_nms_vs_oracle(tracker, tk, oracle, synth, rows, cols, permille):
+    import torch
+    frames = [synth.synth_frame(31 + f, rows, cols, f, 3 * f, -2 * f, permille)[0] for f in range(3)]
+    scale = float(synth.SEMI_SCALE)
+    idx = np.stack([oracle.softmax(scale, s)[0] for s in frames])
+    pr = np.stack([oracle.softmax(scale, s)[1] for s in frames])
+    di, dp = torch.from_numpy(idx.copy()).to(tracker.device), torch.from_numpy(pr.copy()).to(tracker.device)
+    tracker.nms(rows, cols, di, dp)
+    n_sup = 0
+    for f in range(3):
+        mi, pp, n = oracle.nms(rows, cols, idx[f], pr[f])
+        n_sup += n
+        assert (di[f].cpu().numpy() == mi).all() and (bits(dp[f].cpu().numpy()) == bits(pp)).all()
+    assert n_sup > 0 or permille < 200
+    # host-pointer form
+    mi, pp, _ = oracle.nms(rows, cols, idx[0], pr[0])
+    hi, hp = tk.run_nms(rows, cols, idx[0], pr[0])
+    assert (hi == mi).all() and (bits(hp) == bits(pp)).all()

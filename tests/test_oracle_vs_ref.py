@@ -145,3 +145,26 @@ def test_svd3_vs_reference_random(oracle, reference):
         A = (rng.normal(size=(3, 3)) * 10 ** rng.uniform(-2, 2)).astype(np.float32)
         for x, y in zip(oracle.svd3(A), reference.svd3(A)):
             assert (bits(x) == bits(y)).all()
+
+
+@pytest.mark.parametrize("seed,permille", [(1, 140), (2, 400), (3, 700), (4, 1000), (5, 60)])
+def test_nms_restatement_equals_reference_run_nms(oracle, reference, seed, permille):
+    """orc_nms vs the reference's own run_nms.c main() (compiled unmodified into T1): the same
+    suppression events in the same order and the same surviving keypoints."""
+    import maveric_slam_b200  # noqa: F401
+    from maveric_slam_b200 import synth
+    s, _, _ = synth.synth_frame(seed, 24, 80, 0, 0, 0, permille)
+    ev, kp = reference.run_nms(float(synth.SEMI_SCALE), s)
+    idx, pr, _ = oracle.softmax(float(synth.SEMI_SCALE), s)
+    mi, pp, n, ev2 = oracle.nms(24, 80, idx, pr, want_events=True)
+    cells = np.nonzero(mi != 64)[0]
+    kp2 = np.stack([(cells // 24) * 8 + mi[cells] % 8, (cells % 24) * 8 + mi[cells] // 8], axis=1)
+    assert n == len(ev) and np.array_equal(ev, ev2) and np.array_equal(kp, kp2)
+    assert (pp[(mi == 64) & (idx != 64)] == 64.0).all()
+
+
+def test_nms_on_reference_fixture(oracle, reference, image0):
+    ev, kp = reference.run_nms(image0["semi_scale"], image0["semi"])
+    idx, pr, _ = oracle.softmax(float(image0["semi_scale"]), image0["semi"])
+    mi, pp, n, ev2 = oracle.nms(24, 80, idx, pr, want_events=True)
+    assert n == len(ev) > 0 and np.array_equal(ev, ev2)
