@@ -25,6 +25,35 @@ def build(force: bool = False) -> None:
         subprocess.run(["make", "-C", _HERE, "all"], check=True, capture_output=True)
 
 
+def _cpu_model() -> str:
+    """CPU model name + a checksum of its ISA flag set (what -march=native keys on)."""
+    import zlib
+    name, flags = "unknown", ""
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name") and name == "unknown":
+                name = line.split(":", 1)[1].strip()
+            elif line.startswith("flags") and not flags:
+                flags = line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "%s | %08x" % (name, zlib.crc32(flags.encode()))
+
+
+def build_fast() -> None:
+    """libmv_oracle_fast.so is compiled -march=native, so it must be built on the CPU that runs it:
+    a sidecar file records the build host's CPU model + flag set and the library is rebuilt when
+    they differ (the GPU box receives this container's build)."""
+    so = os.path.join(_HERE, "libmv_oracle_fast.so")
+    tag = os.path.join(_HERE, "libmv_oracle_fast.host")
+    here = _cpu_model()
+    built_for = open(tag).read().strip() if os.path.exists(tag) else None
+    stale = (not os.path.exists(so)) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_HERE, "mv_oracle.c"))
+    if stale or built_for != here:
+        subprocess.run(["make", "-C", _HERE, "-B", "libmv_oracle_fast.so"], check=True, capture_output=True)
+        open(tag, "w").write(here)
+
+
 class MatchCfg(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("shift_x", C.c_int), ("shift_y", C.c_int),
                 ("radius", C.c_int), ("max_matches", C.c_int),
@@ -68,6 +97,8 @@ class Oracle:
     """T2: the parametrised restatement."""
 
     def __init__(self, fast: bool = False):
+        if fast:
+            build_fast()
         build()
         self.lib = C.CDLL(os.path.join(_HERE, "libmv_oracle_fast.so" if fast else "libmv_oracle.so"))
         L = self.lib
