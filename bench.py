@@ -321,6 +321,8 @@ def main():
          "peak": fp32_nominal, "unit": "TFLOP/s",
          "frac": (pnp_flops / (pnp_ms * 1e-3) / 1e12) / fp32_nominal if pnp_ms else None,
          "ms_per_launch": pnp_ms, "algorithmic_flops": pnp_flops,
+         "flops_note": "algorithmic = every correspondence in every pass (127 flop per normal-equation pass, 32 per "
+                       "scoring pass); the kernel gates all of them and skips the exact-zero updates of rejected ones",
          "peak_source": "nominal: SMs x 128 FMA/clk x 2 x clocks.max.sm from MEASURED_PEAKS.json "
                         "(FFMA microbenchmark on this pool: 72.9 TFLOP/s, profiles/r01/ffma_peak.txt)",
          "hbm_achieved_gbs": pnp_bytes / (pnp_ms * 1e-3) / 1e9 if pnp_ms else None},

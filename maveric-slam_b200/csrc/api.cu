@@ -816,9 +816,9 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     }
   }
 
-  // The PnP kernel (64 registers x 128 threads) would otherwise take 8 CTAs = the whole register
-  // file of an SM and starve the one-warp row-gather kernel that must run beside it.
-  PnpResidencyCap residency(c, 7);
+  // The PnP kernel (37 KB of shared memory per CTA) would otherwise fill an SM's shared memory with
+  // 6 CTAs and starve the one-warp row-gather kernel (17 KB) that must run beside it.
+  PnpResidencyCap residency(c, 5);
 
   constexpr int NB = 3;  // chunks in flight: staging DMA / row gather / compute
   void *bs[NB], *bd[NB], *bz[NB], *bsc[NB], *dres, *dmoved;
@@ -846,9 +846,9 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   //   copy_stream    DMA of a chunk's logits (and descriptors/depth when not gathering)
   //   stream         in order: detector + row marking of chunk k+1, then match + pose of chunk k
   //   gather_stream  zero-copy pull of chunk k+1's marked descriptor rows, concurrent with the
-  //                  PnP launch of chunk k.  That launch is capped at 7 CTAs per SM (above), which
-  //                  leaves a register slice free; the gather kernel is a one-warp, 32-register
-  //                  CTA that fits in it, so it is resident alongside.
+  //                  PnP launch of chunk k.  That launch is capped at 5 CTAs per SM (above), which
+  //                  leaves registers and 38 KB of shared memory free; the gather kernel is a
+  //                  one-warp CTA that fits in them, so it is resident alongside.
   // whatever the caller queued on the compute stream must be ordered before the staging
   cudaEvent_t start;
   MV_CUDA(c, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));

@@ -645,7 +645,10 @@ static void ne_add_point(ne_acc* acc, const float R[9], const float t[3], const 
   float rv = fmaf(c->fy, b, ncv);
   float e2 = fmaf(rv, rv, ru * ru);
   int w = ok && (!gated || e2 < c->gate_sq);
-  float fx = w ? c->fx : 0.0f, fy = w ? c->fy : 0.0f;
+  acc->cost += w ? e2 : 0.0f;
+  acc->cnt += w;
+  if (!w) return;   /* a correspondence that fails the gate contributes nothing */
+  float fx = c->fx, fy = c->fy;
   float fxa = fx * a, fyb = fy * b, fiz = fx * iz, giz = fy * iz;
   float na = -a, nb = -b, nfy = -fy;
   float u0 = fxa * nb, u1 = fmaf(fxa, a, fx), u2 = fx * nb, u3 = fiz, u5 = fiz * na;
@@ -684,8 +687,6 @@ static void ne_add_point(ne_acc* acc, const float R[9], const float t[3], const 
   g[3] = fmaf(u3, ru, g[3]);
   g[4] = fmaf(v4, rv, g[4]);
   g[5] = fmaf(v5, rv, fmaf(u5, ru, g[5]));
-  acc->cost += w ? e2 : 0.0f;
-  acc->cnt += w;
 }
 
 /* xor-butterfly over L lane partials, the order a shuffle reduction uses */
