@@ -794,6 +794,9 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
                                 (p->pnp.lanes_per_hypothesis == 1 ? 128 : 16);
   int chunk_pairs = 2 * (7 * c->sm_count) / (pnp_ctas_per_pair > 0 ? pnp_ctas_per_pair : 1);
   if (chunk_pairs < 8) chunk_pairs = 8;
+  // short sequences (a rank's shard of a multi-GPU run): at least ~8 chunks, so that the staging
+  // pipeline has something to overlap with instead of one long fill and drain
+  if (chunk_pairs > (n_pairs + 7) / 8) chunk_pairs = (n_pairs + 7) / 8 > 32 ? (n_pairs + 7) / 8 : 32;
   if (const char* e = getenv("MV_HOST_CHUNK_PAIRS")) {  // test hook: force small chunks
     const int v = atoi(e);
     if (v > 0) chunk_pairs = v;
