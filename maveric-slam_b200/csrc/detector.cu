@@ -33,10 +33,94 @@ __device__ __forceinline__ float taylor_exp(const float c[kTaylorTerms], int x) 
   return acc;
 }
 
+// The per-cell part, on a staged tile (see softmax_cells_kernel for the method).  Every thread of
+// the CTA must call it (warp votes inside); `live` threads own a cell.
+__device__ __forceinline__ void softmax_tile_cells(const uint8_t* tile, int n_here, long long cell0,
+                                                   const float* __restrict__ scale, int cells_per_frame,
+                                                   int32_t* __restrict__ max_idx, float* __restrict__ prob,
+                                                   int32_t* __restrict__ num_valid) {
+  const int t = threadIdx.x;
+  const bool live = t < n_here;
+  const long long gc = cell0 + t;
+  // 32-bit division whenever the cell index fits (a 64-bit one costs ~40 instructions per cell)
+  const int frame = !live ? 0
+                    : (gc < 0x7fffffffLL ? (int)((unsigned)gc / (unsigned)cells_per_frame) : (int)(gc / cells_per_frame));
+  float c[kTaylorTerms];
+  taylor_coeffs(__ldg(scale + frame), c);
+
+  // ---- 1. mask of the non-negative channels (bit ch of m2:m1:m0)
+  const int base = t * 65;
+  const int first_word = base >> 2;
+  const int skew = base & 3;                    // the cell starts `skew` bytes into its first word
+  const uint32_t* words = reinterpret_cast<const uint32_t*>(tile);
+  uint32_t m0 = 0, m1 = 0, m2 = 0;
+  if (live) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) {
+      const uint32_t word = words[first_word + w];
+      // sign bits of the four bytes -> bits 0..3 (byte b -> bit b)
+      const uint32_t nib = ((((~word) >> 7) & 0x01010101u) * 0x01020408u) >> 24;
+      if (w < 8) m0 |= nib << (4 * w);
+      else if (w < 16) m1 |= nib << (4 * (w - 8));
+      else m2 |= nib;
+    }
+    // drop the `skew` bytes in front of the cell, keep channels 0..64
+    m0 = __funnelshift_r(m0, m1, skew);
+    m1 = __funnelshift_r(m1, m2, skew);
+    m2 = (m2 >> skew) & 1u;
+  }
+
+  // ---- 2. top_N.c:22-49, candidates in ascending channel order
+  int arg = 64;
+  float top = 0.0f;
+  float denom = FLT_MIN;
+  while (__any_sync(0xffffffffu, (m0 | m1 | m2) != 0)) {
+    int ch = -1;
+    if (m0) { ch = __ffs(m0) - 1; m0 &= m0 - 1; }
+    else if (m1) { ch = 32 + __ffs(m1) - 1; m1 &= m1 - 1; }
+    else if (m2) { ch = 64; m2 = 0; }
+    if (ch >= 0) {
+      const int x = tile[base + ch];            // non-negative int8
+      const float e = taylor_exp(c, x);
+      if (ch != 64 && e > top) {
+        top = e;
+        arg = ch;
+      }
+      denom = __fadd_rn(denom, e);
+    }
+  }
+  if (!live) return;
+  const float p = __fdiv_rn(top, denom);
+  max_idx[gc] = arg;
+  prob[gc] = (arg != 64) ? p : -1.0f;  // top_N.c:156-163
+
+  if (num_valid) {
+    const unsigned active = __activemask();
+    const int lead_frame = __shfl_sync(active, frame, __ffs(active) - 1);
+    const bool uniform = __all_sync(active, frame == lead_frame);
+    if (uniform) {
+      const unsigned votes = __ballot_sync(active, arg != 64);
+      if ((threadIdx.x & 31) == (__ffs(active) - 1) && votes) atomicAdd(num_valid + frame, __popc(votes));
+    } else if (arg != 64) {
+      atomicAdd(num_valid + frame, 1);
+    }
+  }
+}
+
 // One CTA stages 256 consecutive cells (of the flat [n_frames*cells][65] array) into
-// shared memory with 16-byte loads, then one thread walks one cell word by word;
-// words without a non-negative byte (the common case, ~97 % of logits are negative)
-// are skipped with one mask test.
+// shared memory with 16-byte loads; one thread then owns one cell.
+//
+// ~97 % of the logits are negative and skipped by the reference (top_N.c:29), but which ones
+// differs from cell to cell, so walking the 65 bytes and branching per byte makes a warp
+// execute the Taylor exponential once per (lane, byte) pair in turn (measured: 837 warp
+// instructions per 32 cells, issue-bound at 33 % of HBM).  Instead (55 % of HBM; a bulk-async-copy
+// pipelined variant of the same kernel was measured and was not faster -- the rest is the
+// strided shared-memory walk, not the loads):
+//   1. branch-free: the sign bits of the cell's 17 words are compressed into a 65-bit mask of
+//      its non-negative channels (one multiply gathers a word's four sign bits);
+//   2. the warp then loops as often as its busiest lane has candidates (typically 3-6), each
+//      lane taking its next channel in ascending order -- the order the reference adds the
+//      denominator in (top_N.c:26-44) -- so every exponential is evaluated 32 lanes wide.
 template <int kTileCells>  // kTileCells * 65 must be a multiple of 16
 __global__ void __launch_bounds__(kTileCells)
 softmax_cells_kernel(const int8_t* __restrict__ semi, const float* __restrict__ scale,
@@ -62,53 +146,7 @@ softmax_cells_kernel(const int8_t* __restrict__ semi, const float* __restrict__ 
   }
   __syncthreads();
 
-  const int t = threadIdx.x;
-  if (t >= n_here) return;
-  const long long gc = cell0 + t;
-  const int frame = (int)(gc / cells_per_frame);
-  float c[kTaylorTerms];
-  taylor_coeffs(__ldg(scale + frame), c);
-
-  // top_N.c:22-49
-  int arg = 64;
-  float top = 0.0f;
-  float denom = FLT_MIN;
-  const int base = t * 65;
-  const int first_word = base >> 2;
-  const uint32_t* words = reinterpret_cast<const uint32_t*>(tile);
-#pragma unroll 1
-  for (int w = 0; w < 17; w++) {
-    const uint32_t word = words[first_word + w];
-    uint32_t nonneg = ~word & 0x80808080u;
-    while (nonneg) {
-      const int b = (__ffs(nonneg) - 1) >> 3;
-      nonneg &= nonneg - 1;
-      const int ch = ((first_word + w) << 2) + b - base;
-      if (ch < 0 || ch > 64) continue;
-      const int x = (int)((word >> (8 * b)) & 0xFF);
-      const float e = taylor_exp(c, x);
-      if (ch != 64 && e > top) {
-        top = e;
-        arg = ch;
-      }
-      denom = __fadd_rn(denom, e);
-    }
-  }
-  const float p = __fdiv_rn(top, denom);
-  max_idx[gc] = arg;
-  prob[gc] = (arg != 64) ? p : -1.0f;  // top_N.c:156-163
-
-  if (num_valid) {
-    const unsigned active = __activemask();
-    const int lead_frame = __shfl_sync(active, frame, __ffs(active) - 1);
-    const bool uniform = __all_sync(active, frame == lead_frame);
-    if (uniform) {
-      const unsigned votes = __ballot_sync(active, arg != 64);
-      if ((threadIdx.x & 31) == (__ffs(active) - 1) && votes) atomicAdd(num_valid + frame, __popc(votes));
-    } else if (arg != 64) {
-      atomicAdd(num_valid + frame, 1);
-    }
-  }
+  softmax_tile_cells(tile, n_here, cell0, scale, cells_per_frame, max_idx, prob, num_valid);
 }
 
 // ---- K0b -----------------------------------------------------------------
