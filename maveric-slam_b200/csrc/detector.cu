@@ -150,23 +150,27 @@ softmax_cells_kernel(const int8_t* __restrict__ semi, const float* __restrict__ 
 }
 
 // ---- K0b -----------------------------------------------------------------
-// One warp per frame (a one-warp CTA, low profile like the 32-cell softmax): pass 1 counts
-// the valid cells and their prob range, pass 2 is a ballot-ordered compaction of the first
-// top_n cells whose prob clears the interpolated cut.  Selection is sparse (<= top_n of
-// thousands of cells), so a frame is two coalesced sweeps of its 8 B/cell detector output.
-__global__ void __launch_bounds__(32)
+// One CTA per frame: pass 1 counts the valid cells and their prob range (block reduce), pass 2 is
+// a ballot/scan-ordered compaction of the first top_n cells whose prob clears the interpolated
+// cut, 256 cells per round, stopping once top_n are taken.  A frame is two coalesced sweeps of
+// its 8 B/cell detector output.
+constexpr int kTopThreads = 256;
+__global__ void __launch_bounds__(kTopThreads)
 top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob, int cells,
              int top_n, int max_valid, float valid_gt /* round_down(0.01) */,
              int32_t* __restrict__ q_patch, int32_t* __restrict__ q_idx, float* __restrict__ q_prob,
              int32_t* __restrict__ q_count, int32_t* __restrict__ overflow) {
+  __shared__ int s_nv[kTopThreads / 32];
+  __shared__ float s_hi[kTopThreads / 32], s_lo[kTopThreads / 32];
+  __shared__ int s_cnt[kTopThreads / 32];
   const int f = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int32_t* mi = max_idx + (size_t)f * cells;
   const float* pr = prob + (size_t)f * cells;
 
   int nv = 0;
   float hi = 0.0f, lo = FLT_MAX;  // top_N.c:69
-  for (int p = lane; p < cells; p += 32) {
+  for (int p = threadIdx.x; p < cells; p += kTopThreads) {
     const float v = pr[p];
     if (mi[p] != 64 && v > valid_gt) {  // top_N.c:77
       nv++;
@@ -180,8 +184,17 @@ top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob
     hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o));
     lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o));
   }
+  if (lane == 0) { s_nv[wid] = nv; s_hi[wid] = hi; s_lo[wid] = lo; }
+  __syncthreads();
+  nv = 0; hi = 0.0f; lo = FLT_MAX;
+#pragma unroll
+  for (int w = 0; w < kTopThreads / 32; w++) {
+    nv += s_nv[w];
+    hi = fmaxf(hi, s_hi[w]);
+    lo = fminf(lo, s_lo[w]);
+  }
   if (nv >= max_valid) {  // top_N.c:91-94: the reference exits here
-    if (lane == 0) {
+    if (threadIdx.x == 0) {
       q_count[f] = 0;
       if (overflow) overflow[f] = 1;
     }
@@ -197,8 +210,8 @@ top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob
   int32_t* oi = q_idx + (size_t)f * top_n;
   float* opr = q_prob + (size_t)f * top_n;
   int taken = 0;
-  for (int p0 = 0; p0 < cells && taken < top_n; p0 += 32) {  // top_N.c:116-133
-    const int p = p0 + lane;
+  for (int p0 = 0; p0 < cells && taken < top_n; p0 += kTopThreads) {  // top_N.c:116-133
+    const int p = p0 + threadIdx.x;
     int ch = 64;
     float v = 0.0f;
     bool take = false;
@@ -208,15 +221,25 @@ top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob
       take = ch != 64 && v > valid_gt && v >= cut;  // top_N.c:121
     }
     const unsigned votes = __ballot_sync(0xffffffffu, take);
-    const int pos = taken + __popc(votes & ((1u << lane) - 1));
+    if (lane == 0) s_cnt[wid] = __popc(votes);
+    __syncthreads();
+    int before = taken, round = 0;
+#pragma unroll
+    for (int w = 0; w < kTopThreads / 32; w++) {
+      const int c = s_cnt[w];
+      before += w < wid ? c : 0;
+      round += c;
+    }
+    const int pos = before + __popc(votes & ((1u << lane) - 1));
     if (take && pos < top_n) {
       op[pos] = p;
       oi[pos] = ch;
       opr[pos] = v;
     }
-    taken += __popc(votes);
+    taken += round;
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
     q_count[f] = taken < top_n ? taken : top_n;
     if (overflow) overflow[f] = 0;
   }
@@ -249,7 +272,7 @@ extern "C" mv_status mv_top_n_batch(mv_ctx* ctx, int n_frames, int cells, int to
       !d_q_patch || !d_q_idx || !d_q_prob || !d_q_count)
     MV_BAD_ARG(ctx, "mv_top_n_batch");
   mv_prof_scope ps(ctx, "topn");
-  top_n_kernel<<<n_frames, 32, 0, ctx->stream>>>(d_max_idx, d_prob, cells, top_n, max_valid,
+  top_n_kernel<<<n_frames, kTopThreads, 0, ctx->stream>>>(d_max_idx, d_prob, cells, top_n, max_valid,
                                                            mv_round_down(0.01), d_q_patch, d_q_idx,
                                                            d_q_prob, d_q_count, d_overflow);
   MV_CHECK_LAUNCH(ctx);
