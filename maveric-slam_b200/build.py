@@ -60,7 +60,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for l in logs:
             sys.stderr.write(l)
-    if jobs or force or not os.path.exists(OUT):
+    if jobs or force or _newer(objs, OUT):
         # static cudart + libcuda: the library carries its runtime and loads next to
         # torch's own without symbol clashes
         run([NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-cudart", "static"])
