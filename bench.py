@@ -258,6 +258,7 @@ def main():
     prof = {}
     for tag in ["detect", "topn", "match", "emit", "ransac", "gather", "pnp", "pnp_select"]:
         prof[tag] = tr.ctx.profile_read(tag)[0]
+    pnp_accepted = tr.ctx.pnp_work() // 2   # accepted correspondence-passes of one step (two profiled steps)
     tr.ctx.profile(False)
 
     resn = tracking.results_to_numpy(out)
@@ -266,8 +267,18 @@ def main():
     cells = ROWS * COLS
     sm_count = torch.cuda.get_device_properties(dev).multi_processor_count
     fp32_nominal = sm_count * 128 * 2 * sm_max * 1e6 / 1e12   # TFLOP/s, FMA = 2 flops
-    pnp_flops = (count * HYPOTHESES * SAMPLE_ITERS * 8 * FLOPS_NORMAL
-                 + HYPOTHESES * n_corr * (REFINE_ITERS * FLOPS_NORMAL + FLOPS_SCORE))
+    # ALGORITHMIC flops = what the oracle's Gauss-Newton executes: every correspondence is
+    # projected and gated in every pass (FLOPS_SCORE); only an accepted one is accumulated into the normal
+    # equations (FLOPS_NORMAL - FLOPS_SCORE more).  `pnp_accepted` is counted by the kernel in profile mode.
+    # The dense equivalent (every correspondence updates in every pass) is reported beside it.
+    pnp_flops_dense = (count * HYPOTHESES * SAMPLE_ITERS * 8 * FLOPS_NORMAL
+                       + HYPOTHESES * n_corr * (REFINE_ITERS * FLOPS_NORMAL + FLOPS_SCORE))
+    if pnp_accepted > 0:
+        pnp_flops = (count * HYPOTHESES * SAMPLE_ITERS * 8 * FLOPS_NORMAL
+                     + HYPOTHESES * n_corr * (REFINE_ITERS + 1) * FLOPS_SCORE
+                     + pnp_accepted * (FLOPS_NORMAL - FLOPS_SCORE))
+    else:   # kernel forms without the counter (lanes > 1, MV_PNP_FORM=mask|dense)
+        pnp_flops = pnp_flops_dense
     pnp_bytes = 20 * n_corr + 64 * count
     pnp_ms = prof["pnp"]
 
@@ -317,12 +328,16 @@ def main():
     else:
         match_entry = None
     rooflines = [
-        {"kernel": "pnp_gn_kernel<%d> (K3)" % args.lanes, "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
+        {"kernel": ("pnp_gn_sorted_kernel (K3)" if args.lanes == 1 else "pnp_gn_kernel<%d> (K3)" % args.lanes), "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
          "peak": fp32_nominal, "unit": "TFLOP/s",
          "frac": (pnp_flops / (pnp_ms * 1e-3) / 1e12) / fp32_nominal if pnp_ms else None,
          "ms_per_launch": pnp_ms, "algorithmic_flops": pnp_flops,
-         "flops_note": "algorithmic = every correspondence in every pass (127 flop per normal-equation pass, 32 per "
-                       "scoring pass); the kernel gates all of them and skips the exact-zero updates of rejected ones",
+         "flops_note": "algorithmic = the oracle's operation count: 32 flop to project and gate every correspondence in "
+                       "every pass, 95 more for each accepted one in a normal-equation pass (accepted passes counted by "
+                       "the kernel: %d per step = %.1f%% of all); dense_equivalent_flops counts all 127 for every "
+                       "correspondence" % (pnp_accepted, 100.0 * pnp_accepted / max(1, HYPOTHESES * n_corr * REFINE_ITERS)),
+         "dense_equivalent_flops": pnp_flops_dense,
+         "dense_equivalent_TFLOPs": pnp_flops_dense / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
          "peak_source": "nominal: SMs x 128 FMA/clk x 2 x clocks.max.sm from MEASURED_PEAKS.json "
                         "(FFMA microbenchmark on this pool: 72.9 TFLOP/s, profiles/r01/ffma_peak.txt)",
          "hbm_achieved_gbs": pnp_bytes / (pnp_ms * 1e-3) / 1e9 if pnp_ms else None},

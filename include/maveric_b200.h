@@ -49,6 +49,10 @@ unsigned long long mv_ctx_launch_count(mv_ctx* ctx);
  * "gather","pnp","ransac".  Enabled with mv_ctx_profile(ctx, 1). */
 mv_status   mv_ctx_profile(mv_ctx* ctx, int enable);
 mv_status   mv_ctx_profile_read(mv_ctx* ctx, const char* tag, double* avg_ms, int* launches);
+/* Profile mode only: correspondence-passes the Gauss-Newton PnP kernel accepted (and therefore
+ * accumulated into normal equations) in the launches since the last read; the executed-work
+ * figure of bench.py's roofline.  Reading resets the counter. */
+mv_status   mv_ctx_pnp_work(mv_ctx* ctx, unsigned long long* accepted);
 
 /* ------------------------------------------------------------------------- */
 /* Detector post-processing: src/top_N.c                                      */

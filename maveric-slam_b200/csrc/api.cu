@@ -789,10 +789,11 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     MV_BAD_ARG(c, "mv_track_sequence_host");
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
-  // chunk = two full waves of the PnP kernel at its capped residency (7 CTAs/SM, see below)
-  const int pnp_ctas_per_pair = (p->pnp.hypotheses + (p->pnp.lanes_per_hypothesis == 1 ? 127 : 15)) /
-                                (p->pnp.lanes_per_hypothesis == 1 ? 128 : 16);
-  int chunk_pairs = 2 * (7 * c->sm_count) / (pnp_ctas_per_pair > 0 ? pnp_ctas_per_pair : 1);
+  // chunk = two full waves of the PnP kernel at its capped residency (5 CTAs/SM, see below); the
+  // one-thread-per-hypothesis kernel covers 256 hypotheses per CTA, the multi-lane forms 16
+  const int per_cta = p->pnp.lanes_per_hypothesis == 1 ? 256 : 16;
+  const int pnp_ctas_per_pair = (p->pnp.hypotheses + per_cta - 1) / per_cta;
+  int chunk_pairs = 2 * (5 * c->sm_count) / (pnp_ctas_per_pair > 0 ? pnp_ctas_per_pair : 1);
   if (chunk_pairs < 8) chunk_pairs = 8;
   // short sequences (a rank's shard of a multi-GPU run): at least ~8 chunks, so that the staging
   // pipeline has something to overlap with instead of one long fill and drain

@@ -34,6 +34,7 @@ struct mv_ctx {
   char err[512] = {0};
   unsigned long long launches = 0;
   bool profile = false;
+  bool pnp_work_live = false;           // profile mode: the PnP work counter holds launches not yet read
   std::map<std::string, mv_prof_slot> prof;
   std::vector<mv_pending_event> pending;
 

@@ -18,7 +18,7 @@ MV_OK, MV_ERR_NO_DEVICE, MV_ERR_CUDA, MV_ERR_BAD_ARG, MV_ERR_TOO_MANY_VALID = ra
 # Every symbol include/maveric_b200.h and include/maveric_slam_compat.h declare.
 NEW_SYMBOLS = [
     "mv_ctx_create", "mv_ctx_destroy", "mv_ctx_set_stream", "mv_ctx_sync", "mv_last_error", "mv_status_str",
-    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_softmax_batch", "mv_top_n_batch",
+    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_ctx_pnp_work", "mv_softmax_batch", "mv_top_n_batch",
     "compute_softmax_ex", "compute_top_N_ex", "mv_match_params_default", "mv_match_batch",
     "mv_match_pair_host", "mv_ransac_identity_batch", "mv_pnp_params_default", "mv_pnp_gn_batch",
     "mv_build_corr_batch", "mv_track_params_default", "mv_track_sequence", "mv_track_sequence_host",
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     L.mv_ctx_launch_count.restype = C.c_ulonglong
     L.mv_ctx_profile.argtypes = [vp, i32]
     L.mv_ctx_profile_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i32)]
+    L.mv_ctx_pnp_work.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.mv_softmax_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.mv_top_n_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.compute_softmax_ex.argtypes = [vp, f32, vp, i32, C.POINTER(i32), vp, vp]
@@ -183,6 +184,12 @@ class Context:
         n = C.c_int(0)
         self.check(self.lib.mv_ctx_profile_read(self.h, tag.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def pnp_work(self) -> int:
+        """accepted correspondence-passes of the profiled PnP launches since the last read"""
+        v = C.c_ulonglong(0)
+        self.check(self.lib.mv_ctx_pnp_work(self.h, C.byref(v)))
+        return int(v.value)
 
     def close(self) -> None:
         if getattr(self, "h", None):
