@@ -350,12 +350,15 @@ def main():
     step_kernel_ms = sum(v for v in prof.values())
     roofline = dict(rooflines[0])
     roofline["traffic"] = None
+    # DRAM traffic of the dominant kernel from its ncu --set full capture (profiles/ncu_traffic.json holds
+    # dram__bytes_read.sum + dram__bytes_write.sum of one launch and the pairs that launch processed)
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if os.path.exists(tpath):
+    if os.path.exists(tpath) and args.lanes == 1:
         tj = json.load(open(tpath))
-        if tj.get("frames") == n_frames and tj.get("n_gpus", 1) == world:
-            roofline["traffic"] = tj.get("pnp_gn_dram_bytes_per_launch")
-            roofline["traffic_source"] = tj.get("source")
+        per_pair = tj["pnp_gn_dram_bytes_per_launch"] / tj["pairs_per_launch"]
+        roofline["traffic"] = int(per_pair * count)
+        roofline["traffic_source"] = tj.get("source") + " (scaled by pairs per launch: %d -> %d)" % (tj["pairs_per_launch"], count)
+        roofline["algorithmic_bytes"] = pnp_bytes
     roofline["share_of_step"] = pnp_ms / step_kernel_ms if step_kernel_ms else None
 
     # ---- end to end through the host-buffer entry point

@@ -441,3 +441,34 @@ def gather_results(local, n_pairs: int, world: int, group=None):
     out = torch.empty((world * per, 64), dtype=torch.uint8, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:n_pairs]
+
+
+# --------------------------------------------------------------------------------------
+# host side of the host-buffer path: staging memory next to the GPU
+# --------------------------------------------------------------------------------------
+def bind_to_gpu_numa_node(device_index: int):
+    """Restricts this process to the CPUs of the NUMA node GPU `device_index` hangs off, so that the
+    pinned staging buffers it allocates afterwards (first touch) are local to that GPU's PCIe root.
+    One process per GPU (torchrun) is the intended use.  Returns the node number, or None when the
+    platform does not say (single-node hosts, containers without sysfs) -- then nothing changes."""
+    import os
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id  # torch >= 2.5
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = getattr(torch.cuda.get_device_properties(device_index), "pci_device_id", 0)
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None

@@ -1,0 +1,218 @@
+"""GPU parity at BASELINE.json's full sizes, through properties that do not depend on the size
+(the oracle would need minutes there): determinism, equality of the kernel forms, independence of
+a hypothesis from the number of hypotheses, of a pair from its shard / chunk / batch, and of the
+result from the entry point (device-resident vs host buffers).  Everything goes through the C ABI.
+
+  configs[2]  1024 hypotheses x Gauss-Newton over ~1k correspondences
+  configs[3]  KITTI-00-shaped sequence (47x155 cells, ~1k keypoints, 1024 hypotheses), sharded
+  configs[4]  4096 hypotheses (the 16k-keypoint matcher shape is in test_gpu_parity.py)
+"""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROWS, COLS = 47, 155
+
+
+@pytest.fixture(scope="module")
+def tk(tracker):
+    from maveric_slam_b200 import tracking
+    return tracking
+
+
+def _pnp_params(H, lanes=1, seed=0):
+    from maveric_slam_b200 import lib
+    p = lib.PnpParams()
+    lib.load().mv_pnp_params_default(C.byref(p))
+    p.hypotheses, p.lanes_per_hypothesis, p.seed = H, lanes, seed
+    return p
+
+
+def _problems(synth, P, n, stride):
+    corr = np.zeros((P, 5, stride), np.float32)
+    for p in range(P):
+        corr[p], _, _ = synth.synth_pnp_problem(500 + p, n, stride=stride)
+    return corr
+
+
+class _Form:
+    """MV_PNP_FORM for the duration of a block (the library reads it per call)."""
+
+    def __init__(self, form):
+        self.form = form
+
+    def __enter__(self):
+        self.old = os.environ.get("MV_PNP_FORM")
+        os.environ["MV_PNP_FORM"] = self.form
+
+    def __exit__(self, *a):
+        if self.old is None:
+            del os.environ["MV_PNP_FORM"]
+        else:
+            os.environ["MV_PNP_FORM"] = self.old
+
+
+@pytest.mark.parametrize("n,stride", [(1000, 1024), (330, 1024), (513, 640), (31, 32)])
+def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
+    """configs[2]: the sorted kernel (packed gate, per-lane mask walk, per-pass re-deal), the same
+    without the re-deal, the earlier mask kernel and the dense kernel: same bytes for every one of
+    1024 hypotheses and for the selected pose."""
+    import torch
+    P, H = 3, 1024
+    corr = torch.from_numpy(_problems(synth, P, n, stride)).to(tracker.device)
+    cnt = torch.full((P,), n, dtype=torch.int32, device=tracker.device)
+    got = {}
+    for form in ("sorted", "nosort", "mask", "dense"):
+        with _Form(form):
+            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
+            got[form] = (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes())
+    for form in ("nosort", "mask", "dense"):
+        assert got[form] == got["sorted"], form
+
+
+def test_pnp_hypothesis_does_not_depend_on_hypothesis_count(tracker, synth):
+    """configs[4]: 4096 hypotheses.  Hypothesis h is a function of (seed, pair, h) alone, so the first
+    1024 of a 4096-hypothesis run are the 1024-hypothesis run, bit for bit, and the selected pose is
+    the best key (inliers, then cost, then index) over the per-hypothesis records."""
+    import torch
+    P, n, stride = 2, 1000, 1024
+    corr = torch.from_numpy(_problems(synth, P, n, stride)).to(tracker.device)
+    cnt = torch.full((P,), n, dtype=torch.int32, device=tracker.device)
+    pose4, stats4, hyp4 = tracker.pnp_gn(_pnp_params(4096), corr, cnt, want_hyp=True)
+    pose1, stats1, hyp1 = tracker.pnp_gn(_pnp_params(1024), corr, cnt, want_hyp=True)
+    hyp4, hyp1 = hyp4.cpu().numpy(), hyp1.cpu().numpy()
+    assert hyp4[:, :1024].tobytes() == hyp1.tobytes()
+    stats4, pose4 = stats4.cpu().numpy(), pose4.cpu().numpy()
+    for p in range(P):
+        inl = hyp4[p, :, 7]
+        best = inl.max()
+        assert stats4[p, 0] == best and stats4[p, 3] == 1
+        h = int(stats4[p, 2])
+        assert inl[h] == best and (pose4[p] == hyp4[p, h, :7]).all()
+        # a 4096-hypothesis search cannot end below the 1024-hypothesis one
+        assert best >= stats1.cpu().numpy()[p, 0]
+
+
+def test_pnp_pair_does_not_depend_on_batch(tracker, synth):
+    """A pair's result depends on its global pair index only: a batch of 6 equals two batches of 3
+    with first_pair = 0 and 3 (what sharding across GPUs and chunked staging rely on)."""
+    import torch
+    P, n, stride, H = 6, 700, 1024, 512
+    corr = torch.from_numpy(_problems(synth, P, n, stride)).to(tracker.device)
+    cnt = torch.full((P,), n, dtype=torch.int32, device=tracker.device)
+    pose, stats, _ = tracker.pnp_gn(_pnp_params(H), corr, cnt)
+    parts = []
+    for first in (0, 3):
+        prm = _pnp_params(H)
+        prm.first_pair = first
+        pp, ss, _ = tracker.pnp_gn(prm, corr[first:first + 3].contiguous(), cnt[first:first + 3].contiguous())
+        parts.append((pp.cpu().numpy(), ss.cpu().numpy()))
+    assert np.concatenate([a for a, _ in parts]).tobytes() == pose.cpu().numpy().tobytes()
+    assert np.concatenate([b for _, b in parts]).tobytes() == stats.cpu().numpy().tobytes()
+
+
+def test_pnp_ragged_counts_and_work_counter(tracker, synth):
+    """Pairs of one launch with 0, 1, 8, 511, 512, 513 and 1024 correspondences (empty, below the
+    minimal sample, around the staging chunk of 512, full): each equals its own single-pair launch;
+    the profile-mode work counter never exceeds hypotheses x correspondences x passes."""
+    import torch
+    counts = [0, 1, 8, 511, 512, 513, 1024]
+    stride, H = 1024, 256
+    corr = np.zeros((len(counts), 5, stride), np.float32)
+    for p, n in enumerate(counts):
+        if n:
+            corr[p, :, :n] = synth.synth_pnp_problem(900 + p, n, stride=n)[0]
+    dcorr = torch.from_numpy(corr).to(tracker.device)
+    dcnt = torch.tensor(counts, dtype=torch.int32, device=tracker.device)
+    tracker.ctx.profile(True)
+    tracker.ctx.pnp_work()
+    pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), dcorr, dcnt, want_hyp=True)
+    work = tracker.ctx.pnp_work()
+    tracker.ctx.profile(False)
+    assert 0 < work <= H * sum(counts) * 10
+    pose, stats = pose.cpu().numpy(), stats.cpu().numpy()
+    assert stats[0, 3] == 0 and (pose[0] == np.array([1, 0, 0, 0, 0, 0, 0], np.float32)).all()
+    for p, n in enumerate(counts):
+        prm = _pnp_params(H)
+        prm.first_pair = p
+        p1, s1, _ = tracker.pnp_gn(prm, dcorr[p:p + 1].contiguous(), dcnt[p:p + 1].contiguous())
+        assert p1.cpu().numpy().tobytes() == pose[p:p + 1].tobytes(), n
+        assert s1.cpu().numpy().tobytes() == stats[p:p + 1].tobytes(), n
+
+
+def test_sequence_full_config_properties(tracker, tk, synth):
+    """configs[3] at its real parameters (47x155 cells, top-1000 queries, 1024 matches, 1024
+    hypotheses), 97 frames: two runs are identical (determinism); two shards with one halo frame
+    and first_pair = 0 / 48 reproduce the unsharded records (multi-GPU sharding); the host-buffer
+    entry point, unchunked and in chunks of 7 pairs, returns the same bytes (e2e path); both
+    matchers agree."""
+    import torch
+    n_frames, seed = 97, 0
+    off = synth.default_offsets(n_frames, seed)
+    semi, desc, depth = tracker.synth_frames(seed, ROWS, COLS, 0, off)
+    scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+
+    def params(first=0, tc=True):
+        return tk.kitti_track_params(top_n=1000, max_valid=8192, max_matches=1024, hypotheses=1024, refine_iters=10,
+                                     sample_iters=4, seed=0, first_pair=first, lanes=1, use_tensor_cores=tc)
+
+    full = tracker.track_sequence(params(), semi, scale, desc, depth).cpu().numpy()
+    again = tracker.track_sequence(params(), semi, scale, desc, depth).cpu().numpy()
+    assert full.tobytes() == again.tobytes()
+    res = tk.results_to_numpy(torch.from_numpy(full))
+    assert (res["status"] == 0).all() and (res["num_matches"] > 100).all() and (res["pnp_inliers"] > 20).all()
+
+    a = tracker.track_sequence(params(0), semi[:49], scale[:49], desc[:49], depth[:49]).cpu().numpy()
+    b = tracker.track_sequence(params(48), semi[48:], scale[48:], desc[48:], depth[48:]).cpu().numpy()
+    assert np.concatenate([a, b]).tobytes() == full.tobytes()
+
+    dp4a = tracker.track_sequence(params(tc=False), semi, scale, desc, depth).cpu().numpy()
+    assert dp4a.tobytes() == full.tobytes()
+
+    hs = torch.empty(semi.shape, dtype=torch.int8, pin_memory=True).copy_(semi)
+    hd = torch.empty(desc.shape, dtype=torch.int8, pin_memory=True).copy_(desc)
+    hz = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True).copy_(depth)
+    hsc = torch.empty(scale.shape, dtype=torch.float32, pin_memory=True).copy_(scale)
+    torch.cuda.synchronize()
+    host, up, down = tracker.track_sequence_host(params(), hs, hsc, hd, hz)
+    assert host.tobytes() == full.tobytes() and down == 64 * (n_frames - 1)
+    # selective staging moves the logits, the depth and only the descriptor rows the matcher reads
+    assert up < semi.numel() + 4 * depth.numel() + desc.numel() // 2
+    os.environ["MV_HOST_CHUNK_PAIRS"] = "7"
+    try:
+        chunked, _, _ = tracker.track_sequence_host(params(), hs, hsc, hd, hz)
+    finally:
+        del os.environ["MV_HOST_CHUNK_PAIRS"]
+    assert chunked.tobytes() == full.tobytes()
+
+
+def test_trajectory_chain_is_associative(tracker, tk):
+    """Pose chaining (compute_trajectory.py:76-77: R_k ... R_1, t_1 + ... + t_k) over 4540
+    transforms, the length of configs[3]: chaining the whole list equals chaining its second half
+    on top of the last pose of its first half."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, cut = 4540, 2000
+    T = np.zeros((n, 3, 4))
+    for i in range(n):
+        w = rng.normal(size=3) * 0.01
+        th = np.linalg.norm(w)
+        k = w / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        T[i, :, :3] = np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+        T[i, :, 3] = rng.normal(size=3) * 0.5
+
+    def chain(x):
+        return tracker.chain_transforms(torch.from_numpy(np.ascontiguousarray(x)).to(tracker.device)).cpu().numpy()
+
+    whole, first, second = chain(T), chain(T[:cut]), chain(T[cut:])
+    assert whole.shape == (n + 1, 3, 4) and (whole[0] == np.eye(4)[:3]).all()
+    assert np.abs(whole[:cut + 1] - first).max() < 1e-11
+    R = second[:, :, :3] @ first[-1, :, :3]
+    t = second[:, :, 3] + first[-1, :, 3]
+    assert np.abs(whole[cut:, :, :3] - R).max() < 1e-11
+    assert np.abs(whole[cut:, :, 3] - t).max() < 1e-9 * max(1.0, np.abs(t).max())
