@@ -907,6 +907,8 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   // queued on the same SM stretch its global loads; the pose kernel (FP32-bound, its inputs in
   // shared memory) does not care.
   int pending_gather = -1;
+  // MV_HOST_EAGER_GATHER=1: start a chunk's row gather as soon as its detector is done (A/B knob)
+  const bool eager_gather = getenv("MV_HOST_EAGER_GATHER") && atoi(getenv("MV_HOST_EAGER_GATHER"));
   cudaEvent_t matched;
   MV_CUDA(c, cudaEventCreateWithFlags(&matched, cudaEventDisableTiming));
   auto launch_gather = [&](int k, cudaEvent_t after) -> mv_status {
@@ -949,8 +951,8 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     mark("det_end", k, c->stream);
     if (!gather) {
       MV_CUDA(c, cudaEventRecord(ready[b], c->stream));
-    } else if (k == 0) {
-      return launch_gather(0, nullptr);
+    } else if (k == 0 || eager_gather) {
+      return launch_gather(k, nullptr);
     } else {
       pending_gather = k;   // released by chunk k-1's matcher, see stage_compute
     }

@@ -252,6 +252,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       if (t.n_rows == 0) continue;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
       mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5, 512);
+#ifdef MV_TC_TRACE
+      const long long cq0 = clock64();
+#endif
 
       // validity words of the tile's cell range (plus the overrun of the last chunk)
       const int w_lo = (t.X0 * g.rows) >> 5;
@@ -357,6 +360,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       }
       fence_proxy_async_smem();
       mbar_arrive(smem_u32(&bar_full_a[a]));
+#ifdef MV_TC_TRACE
+      if (row == 0) MV_TC_TRACE_ADD(8, cq0);
+#endif
       tile++;
     }
   } else {
@@ -367,7 +373,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
     const int row = qd * 32 + lane;
     uint32_t chunk = 0, tile = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
+#ifdef MV_TC_TRACE
+      const long long cs0 = clock64();
+#endif
       const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+#ifdef MV_TC_TRACE
+      if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(11, cs0);
+      const long long cp0 = clock64();
+#endif
       if (t.n_rows == 0) continue;
       const int pair = item / g.tiles_per_pair;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
@@ -395,9 +408,21 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       }
 
       // ---- the tile's chunks
+#ifdef MV_TC_TRACE
+      if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(13, cp0);
+#endif
       for (int c = 0; c < t.n_chunks; c++, chunk++) {
         const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
+#ifdef MV_TC_TRACE
+        const long long cw0 = clock64();
+#endif
         mbar_wait(smem_u32(&bar_acc_full[acc]), accph, abort_flag, 7);
+#ifdef MV_TC_TRACE
+        if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(14, cw0);
+#endif
+#ifdef MV_TC_TRACE
+        const long long ce0 = clock64();
+#endif
         tc_fence_after();
         const int chunk_x0 = t.X0 + c * g.cx;
         const int chunk_cell = chunk_x0 * g.rows;
@@ -472,10 +497,16 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         }
         tc_fence_before();
         __syncwarp();
+#ifdef MV_TC_TRACE
+        if (lane == 0) MV_TC_TRACE_ADD(9 + (ew == 0 ? 0 : 1), ce0);
+#endif
         if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
       }
 
       // ---- merge the row's two threads: larger score, ties to the earlier cell
+#ifdef MV_TC_TRACE
+      const long long cm0 = clock64();
+#endif
       MergeSlot* mslot = sM + (tile & 1) * kTileQ + row;
       if (half == 1) { mslot->s = bs; mslot->cell = bcell; }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
@@ -488,6 +519,9 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         best_score[out] = bs;
       }
       __syncwarp();
+#ifdef MV_TC_TRACE
+      if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(12, cm0);
+#endif
       if (lane == 0) mbar_arrive(smem_u32(&bar_empty_a[a]));
       tile++;
     }
@@ -496,6 +530,19 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
+#ifdef MV_TC_TRACE
+  if (threadIdx.x == 0) {
+    const unsigned long long done = atomicAdd(&mv_tc_trace[15], 1ull) + 1;
+    if (done == gridDim.x) {
+      printf("tc trace (Mcycles summed over grid): empty_b %.2f full_a(mma) %.2f acc_empty %.2f full_b %.2f empty_a(query) %.2f "
+             "full_a(epi, x256 thr) %.2f acc_full(epi, x256 thr) %.2f | query tile body %.2f epi chunk w6 %.2f epi chunk others(x7) %.2f | epi w6: tile_span %.2f merge+store %.2f prechunk(full_a wait, row info) %.2f acc_full wait w6 %.2f items %d\n",
+             mv_tc_trace[1] * 1e-6, mv_tc_trace[2] * 1e-6, mv_tc_trace[3] * 1e-6, mv_tc_trace[4] * 1e-6, mv_tc_trace[5] * 1e-6 / 128,
+             mv_tc_trace[6] * 1e-6 / 256, mv_tc_trace[7] * 1e-6 / 256, mv_tc_trace[8] * 1e-6, mv_tc_trace[9] * 1e-6,
+             mv_tc_trace[10] * 1e-6 / 7, mv_tc_trace[11] * 1e-6, mv_tc_trace[12] * 1e-6, mv_tc_trace[13] * 1e-6, mv_tc_trace[14] * 1e-6, g.n_items);
+      for (int i = 0; i < 16; i++) mv_tc_trace[i] = 0;
+    }
+  }
+#endif
 }
 
 }  // namespace

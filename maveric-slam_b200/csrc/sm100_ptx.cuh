@@ -48,11 +48,21 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 }
 // `backoff_ns` > 0: sleep between probes -- for producer-side waits (a free slot), which are long
 // and off the critical path; a spinning warp would otherwise take issue slots from the epilogue.
+#ifdef MV_TC_TRACE
+// debug build (-DMV_TC_TRACE): cycles spent in every wait site, summed over the grid
+__device__ unsigned long long mv_tc_trace[16];
+#define MV_TC_TRACE_ADD(who, c0) atomicAdd(&mv_tc_trace[(who)], (unsigned long long)(clock64() - (c0)))
+#else
+#define MV_TC_TRACE_ADD(who, c0)
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* abort_flag, int who,
                                           unsigned backoff_ns = 0) {
   uint64_t t0 = 0;
+#ifdef MV_TC_TRACE
+  const long long c0 = clock64();
+#endif
   for (uint32_t i = 1;; i++) {
-    if (mbar_try_wait(bar, parity)) return;
+    if (mbar_try_wait(bar, parity)) { MV_TC_TRACE_ADD(who, c0); return; }
     if (backoff_ns) __nanosleep(backoff_ns);
     if ((i & 255u) == 0) {
       const uint64_t t = globaltimer_ns();
