@@ -285,6 +285,23 @@ typedef struct {
 mv_status mv_synth_frames(mv_ctx* ctx, const mv_synth_params* p, int first_frame, int n_frames,
                           const int32_t* d_off, int8_t* d_semi, int8_t* d_desc, float* d_depth);
 
+/* ------------------------------------------------------------------------- */
+/* Local bundle adjustment: src/local_bundle_adjustment.c   */
+/* ------------------------------------------------------------------------- */
+
+/* The Schur complement of the landmarks of `n_windows` independent windows, as main() of
+ * local_bundle_adjustment.c:133-246 computes it for one: per (landmark, pose) factor the
+ * 10 x 10 product [J|r]^T [J|r] scattered into the landmark / pose-landmark / pose blocks
+ * (:152-224), 3 x 3 block inversion (:227), C -= B A^-1 B^T per chunk of landmarks (:229-245),
+ * every fp32 sum in the reference's order.
+ *   d_J  float [n_windows][n_ldmks][n_poses][20]  factor blocks as the reference stores them:
+ *        2 x 10 column-major, columns dLandmark(3) | dPose(6) | residual(1)
+ *   d_C  float [n_windows][(6 n_poses + 1)^2]     reduced camera matrix, column-major, last row
+ *        = J^T r of the poses (what the reference hands to its unimplemented cholesky(), :247)
+ * n_ldmks must be a multiple of chunk (the reference: 1000 landmarks, 8 poses, chunks of 4). */
+mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
+                             const float* d_J, float* d_C);
+
 #ifdef __cplusplus
 }
 #endif

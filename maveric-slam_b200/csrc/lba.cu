@@ -1,0 +1,175 @@
+// lba.cu -- local bundle adjustment: Schur complement of the landmarks, batched over windows
+// (reference: src/local_bundle_adjustment.c:133-246).
+//
+// The reference walks the landmarks of one window in chunks of 4: every (landmark, pose) factor's
+// [J|r]^T [J|r] (10 x 10, from a 2 x 10 Jacobian block) is scattered into the landmark block
+// diagonal A, the pose-landmark block B and the pose block C; A is inverted 3 x 3 block by block
+// and C -= B A^-1 B^T.  All of it is fp32 whose result depends on the order of the additions
+// (chunk after chunk into C, pose after pose into A, k innermost in the shim's matmul2), so the
+// order is part of the contract.  Here one CTA owns one window and keeps C, A, B, B A^-1 and the
+// chunk's factor products in shared memory; a chunk is five barrier-separated phases in which
+// every thread owns whole output entries and adds their terms in the reference's order -- the
+// parallelism is across entries (2 304 of C per chunk) and across windows, never inside a sum.
+// Bit-identical to the reference program on its own input and on substituted inputs
+// (tests/test_lba.py, oracle/ref_harness.c).
+//
+// Bound: HBM.  A window reads 80 B per factor (640 KB for 1000 landmarks x 8 poses) and writes
+// (6P+1)^2 floats; the arithmetic is ~150 flop per factor-byte-free entry and latency-bound per
+// CTA (dependent additions), so throughput comes from the number of resident windows.
+#include "mv_common.cuh"
+
+namespace {
+
+constexpr int kLbaThreads = 256;
+
+// local_bundle_adjustment.c:48-75, operation for operation (no FMA: the file is built -fmad=false)
+__device__ __forceinline__ void invert_3x3(float* matrix, int stride) {
+  float m[9], inv[9];
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) m[j * 3 + i] = matrix[j * stride + i];
+  const float det = __fadd_rn(__fsub_rn(__fmul_rn(m[0], __fsub_rn(__fmul_rn(m[4], m[8]), __fmul_rn(m[5], m[7]))),
+                                        __fmul_rn(m[1], __fsub_rn(__fmul_rn(m[3], m[8]), __fmul_rn(m[5], m[6])))),
+                              __fmul_rn(m[2], __fsub_rn(__fmul_rn(m[3], m[7]), __fmul_rn(m[4], m[6]))));
+  inv[0] = __fdiv_rn(__fsub_rn(__fmul_rn(m[4], m[8]), __fmul_rn(m[5], m[7])), det);
+  inv[1] = __fdiv_rn(__fsub_rn(__fmul_rn(m[2], m[7]), __fmul_rn(m[1], m[8])), det);
+  inv[2] = __fdiv_rn(__fsub_rn(__fmul_rn(m[1], m[5]), __fmul_rn(m[2], m[4])), det);
+  inv[3] = __fdiv_rn(__fsub_rn(__fmul_rn(m[5], m[6]), __fmul_rn(m[3], m[8])), det);
+  inv[4] = __fdiv_rn(__fsub_rn(__fmul_rn(m[0], m[8]), __fmul_rn(m[2], m[6])), det);
+  inv[5] = __fdiv_rn(__fsub_rn(__fmul_rn(m[2], m[3]), __fmul_rn(m[0], m[5])), det);
+  inv[6] = __fdiv_rn(__fsub_rn(__fmul_rn(m[3], m[7]), __fmul_rn(m[4], m[6])), det);
+  inv[7] = __fdiv_rn(__fsub_rn(__fmul_rn(m[1], m[6]), __fmul_rn(m[0], m[7])), det);
+  inv[8] = __fdiv_rn(__fsub_rn(__fmul_rn(m[0], m[4]), __fmul_rn(m[1], m[3])), det);
+#pragma unroll
+  for (int j = 0; j < 3; j++)
+#pragma unroll
+    for (int i = 0; i < 3; i++) matrix[j * stride + i] = inv[j * 3 + i];
+}
+
+// One CTA per window.  Shared memory: Jc[nf*20] Hs[nf*100] C[SH*SH] A[LD*LD] B[SH*LD] BA[SH*LD]
+__global__ void __launch_bounds__(kLbaThreads)
+lba_schur_kernel(int n_ldmks, int n_poses, int chunk, const float* __restrict__ J_all, float* __restrict__ C_all) {
+  extern __shared__ __align__(16) float lba_smem[];
+  const int PD = 6 * n_poses, SH = PD + 1, LD = 3 * chunk, nf = chunk * n_poses;
+  float* Jc = lba_smem;            // first: filled with 16-byte stores
+  float* Hs = Jc + nf * 20;
+  float* C = Hs + nf * 100;
+  float* A = C + SH * SH;
+  float* B = A + LD * LD;
+  float* BA = B + SH * LD;
+  const int tid = threadIdx.x;
+  const float* J = J_all + (size_t)blockIdx.x * n_ldmks * n_poses * 20;
+
+  for (int e = tid; e < SH * SH; e += kLbaThreads) C[e] = 0.0f;
+  for (int e = tid; e < LD * LD; e += kLbaThreads) A[e] = 0.0f;
+  for (int e = tid; e < SH * LD; e += kLbaThreads) BA[e] = 0.0f;
+  float hprev = 0.0f;   // entry tid of the previous factor's product (the shim's 0 * D, :166-172)
+
+  for (int c0 = 0; c0 < n_ldmks; c0 += chunk) {
+    // ---- phase 0: the chunk's factors; A's diagonal blocks and B start at zero (:141-143)
+    {
+      const float4* src = reinterpret_cast<const float4*>(J + (size_t)c0 * n_poses * 20);
+      float4* dst = reinterpret_cast<float4*>(Jc);
+      for (int e = tid; e < nf * 5; e += kLbaThreads) dst[e] = __ldg(src + e);
+      for (int e = tid; e < chunk * 9; e += kLbaThreads) {
+        const int I = (e / 9) * 3, i = (e % 9) / 3, j = e % 3;
+        A[(I + i) * LD + I + j] = 0.0f;
+      }
+      for (int e = tid; e < SH * LD; e += kLbaThreads) B[e] = 0.0f;
+    }
+    __syncthreads();
+    // ---- phase 1: H = [J|r]^T [J|r] per factor, entry (i, j) by thread 10 i + j, factors in
+    // the reference's order (landmark of the chunk outer, pose inner); each product starts as
+    // 0 * (the previous factor's entry), so a non-finite entry sticks exactly as it does there
+    if (tid < 100) {
+      const int i = tid / 10, j = tid % 10;
+      for (int f = 0; f < nf; f++) {
+        const float* Jf = Jc + f * 20;
+        float h = __fmul_rn(0.0f, hprev);
+        h = __fadd_rn(h, __fmul_rn(Jf[i * 2], Jf[j * 2]));
+        h = __fadd_rn(h, __fmul_rn(Jf[i * 2 + 1], Jf[j * 2 + 1]));
+        Hs[f * 100 + tid] = h;
+        hprev = h;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: scatter (:176-219).  H is addressed column-major with stride 10, as there.
+    {
+      const int nA = chunk * 9, nB = nf * 18, nBf = chunk * 3, nC = n_poses * 36, nCf = n_poses * 6;
+      for (int e = tid; e < nA + nB + nBf + nC + nCf; e += kLbaThreads) {
+        if (e < nA) {                                    // H_LL: sum over poses
+          const int ci = e / 9, j = (e % 9) / 3, i = e % 3, li = ci * 3;
+          float v = A[(li + j) * LD + li + i];
+          for (int p = 0; p < n_poses; p++) v = __fadd_rn(Hs[(ci * n_poses + p) * 100 + j * 10 + i], v);
+          A[(li + j) * LD + li + i] = v;
+        } else if (e < nA + nB) {                        // H_PL: one factor each
+          const int q = e - nA, f = q / 18, j = (q % 18) / 6, i = q % 6;
+          const int ci = f / n_poses, p = f % n_poses;
+          float* b = B + p * 6 + i + (ci * 3 + j) * SH;
+          *b = __fadd_rn(Hs[f * 100 + j * 10 + 3 + i], *b);
+        } else if (e < nA + nB + nBf) {                  // landmark gradient row: sum over poses
+          const int q = e - nA - nB, ci = q / 3, j = q % 3;
+          float* b = B + (ci * 3 + j) * SH + SH - 1;
+          float v = *b;
+          for (int p = 0; p < n_poses; p++) v = __fadd_rn(Hs[(ci * n_poses + p) * 100 + j * 10 + 9], v);
+          *b = v;
+        } else if (e < nA + nB + nBf + nC) {             // H_PP: sum over the chunk's landmarks
+          const int q = e - nA - nB - nBf, p = q / 36, j = (q % 36) / 6, i = q % 6;
+          float* c = C + (p * 6 + j) * SH + p * 6 + i;
+          float v = *c;
+          for (int ci = 0; ci < chunk; ci++) v = __fadd_rn(Hs[(ci * n_poses + p) * 100 + (3 + j) * 10 + 3 + i], v);
+          *c = v;
+        } else {                                         // pose gradient row
+          const int q = e - nA - nB - nBf - nC, p = q / 6, j = q % 6;
+          float* c = C + (p * 6 + j) * SH + SH - 1;
+          float v = *c;
+          for (int ci = 0; ci < chunk; ci++) v = __fadd_rn(Hs[(ci * n_poses + p) * 100 + (3 + j) * 10 + 9], v);
+          *c = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: A^-1, block by block (:227)
+    if (tid < chunk) invert_3x3(A + (tid * 3) * LD + tid * 3, LD);
+    __syncthreads();
+    // ---- phase 4: (B A^-1)^T = A^-T B^T as the shim computes it (:230-235): 0 * old + sum over k
+    for (int e = tid; e < LD * PD; e += kLbaThreads) {
+      const int i = e / PD, j = e % PD;
+      float v = __fmul_rn(0.0f, BA[i * SH + j]);
+      for (int k = 0; k < LD; k++) v = __fadd_rn(v, __fmul_rn(A[i * LD + k], B[k * SH + j]));
+      BA[i * SH + j] = v;
+    }
+    __syncthreads();
+    // ---- phase 5: C -= B A^-1 B^T (:238-243): 1 * old, then (-1 * b) * ba for k ascending
+    for (int e = tid; e < PD * PD; e += kLbaThreads) {
+      const int i = e / PD, j = e % PD;
+      float v = C[i * SH + j];
+      for (int k = 0; k < LD; k++) v = __fadd_rn(v, __fmul_rn(-B[k * SH + i], BA[k * SH + j]));
+      C[i * SH + j] = v;
+    }
+    __syncthreads();
+  }
+  float* out = C_all + (size_t)blockIdx.x * SH * SH;
+  for (int e = tid; e < SH * SH; e += kLbaThreads) out[e] = C[e];
+}
+
+}  // namespace
+
+extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
+                                        const float* d_J, float* d_C) {
+  if (!ctx) return MV_ERR_BAD_ARG;
+  if (n_windows <= 0 || n_ldmks <= 0 || n_poses <= 0 || chunk <= 0 || !d_J || !d_C)
+    MV_BAD_ARG(ctx, "mv_lba_schur_batch");
+  if (n_ldmks % chunk != 0 || n_poses > 16 || chunk > 16)
+    MV_BAD_ARG(ctx, "mv_lba_schur_batch: n_ldmks a multiple of chunk, n_poses <= 16, chunk <= 16");
+  const int PD = 6 * n_poses, SH = PD + 1, LD = 3 * chunk, nf = chunk * n_poses;
+  const size_t smem = sizeof(float) * ((size_t)SH * SH + (size_t)LD * LD + 2 * (size_t)SH * LD + (size_t)nf * 120);
+  if (smem > 200 * 1024) MV_BAD_ARG(ctx, "mv_lba_schur_batch: window too large for shared memory");
+  if (smem > 48 * 1024)
+    MV_CUDA(ctx, cudaFuncSetAttribute(lba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mv_prof_scope ps(ctx, "lba");
+  lba_schur_kernel<<<n_windows, kLbaThreads, smem, ctx->stream>>>(n_ldmks, n_poses, chunk, d_J, d_C);
+  MV_CHECK_LAUNCH(ctx);
+  return MV_OK;
+}

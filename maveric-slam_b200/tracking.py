@@ -368,6 +368,18 @@ class Tracker:
         self.ctx.check(self.lib.mv_results_to_transforms(self.ctx.h, n, self._d(results), self._d(T)))
         return T
 
+    def lba_schur(self, J, chunk: int = 4):
+        """src/local_bundle_adjustment.c:133-246 for a batch of windows: float32
+        [n_windows, n_ldmks, n_poses, 20] factor blocks (device) -> float32
+        [n_windows, 6 n_poses + 1, 6 n_poses + 1] reduced camera matrices, stored column-major as in
+        the reference (so [w, c, r] is row r, column c)."""
+        torch = self.torch
+        n_w, n_l, n_p, _ = J.shape
+        sh = 6 * n_p + 1
+        out = torch.empty((n_w, sh, sh), dtype=torch.float32, device=self.device)
+        self.ctx.check(self.lib.mv_lba_schur_batch(self.ctx.h, n_w, n_l, n_p, chunk, self._d(J), self._d(out)))
+        return out
+
     def chain_transforms(self, transforms):
         """python/compute_trajectory.py:49-51,76-77 as a parallel scan: float64 [n, 3, 4] relative
         transforms -> float64 [n+1, 3, 4] frame poses, pose 0 the identity."""

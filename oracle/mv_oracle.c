@@ -608,6 +608,79 @@ void orc_matmul2(size_t I, size_t J, size_t K, const float* A, const float* B,
 }
 
 /* ===================================================================== */
+/* Local bundle adjustment: Schur complement of the landmarks              */
+/* (src/local_bundle_adjustment.c:133-246)              */
+/* ===================================================================== */
+
+/* local_bundle_adjustment.c:48-75: cofactors over the determinant, each quotient on its own */
+void orc_invert_3x3(float* matrix, int stride) {
+  float m[9], inv[9];
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) m[j * 3 + i] = matrix[j * stride + i];
+  float det = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+              m[2] * (m[3] * m[7] - m[4] * m[6]);
+  inv[0] = (m[4] * m[8] - m[5] * m[7]) / det;
+  inv[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+  inv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  inv[3] = (m[5] * m[6] - m[3] * m[8]) / det;
+  inv[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+  inv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+  inv[6] = (m[3] * m[7] - m[4] * m[6]) / det;
+  inv[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+  inv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+  for (int j = 0; j < 3; j++)
+    for (int i = 0; i < 3; i++) matrix[j * stride + i] = inv[j * 3 + i];
+}
+
+/* local_bundle_adjustment.c:35-46 with alpha = beta = 1, as every call site has it */
+static void lba_add(const float* A, float* B, int rows, int cols, int sA, int sB) {
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) B[j * sB + i] = 1.0f * A[j * sA + i] + 1.0f * B[j * sB + i];
+}
+
+/* The reduced camera matrix of one window: for every chunk of `chunk` landmarks, the factors'
+ * [J|r]^T [J|r] blocks are scattered into the landmark block diagonal A, the pose-landmark block B
+ * and the pose block C (:152-224), A is inverted block by block (:227), and C -= B A^-1 B^T
+ * (:229-245).  C is (6 n_poses + 1)^2, column-major, its last row carrying J^T r (the last
+ * column stays 0, as in the reference).
+ *   J  [n_ldmks][n_poses][20]: the factor of (landmark, pose) as the reference stores it, a 2 x 10
+ *      column-major block [dLandmark(3) | dPose(6) | residual(1)].
+ * The reference's scratch persists across chunks and that is reproduced: off-diagonal blocks of A
+ * stay 0, B A^-1 is overwritten as 0 * old + sum (so a non-finite entry sticks).  Its H_factor is
+ * uninitialised stack before the first 0 * old; here it starts at 0.  n_ldmks % chunk == 0. */
+void orc_lba_schur(int n_ldmks, int n_poses, int chunk, const float* J, float* C) {
+  const int PD = 6 * n_poses, SH = PD + 1, LD = 3 * chunk;
+  float* A = (float*)calloc((size_t)LD * LD, sizeof(float));
+  float* B = (float*)calloc((size_t)SH * LD, sizeof(float));
+  float* BA = (float*)calloc((size_t)SH * LD, sizeof(float));
+  float H[100];
+  memset(H, 0, sizeof(H));
+  memset(C, 0, sizeof(float) * (size_t)SH * SH);
+  for (int c0 = 0; c0 < n_ldmks; c0 += chunk) {
+    for (int I = 0; I < LD; I += 3)                       /* :120-129 */
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) A[(I + i) * LD + I + j] = 0;
+    memset(B, 0, sizeof(float) * (size_t)SH * LD);
+    for (int ci = 0; ci < chunk; ci++) {
+      for (int p = 0; p < n_poses; p++) {
+        const int pi = p * 6, li = ci * 3;
+        const float* Jf = J + ((size_t)(c0 + ci) * n_poses + p) * 20;
+        orc_matmul2(10, 10, 2, Jf, Jf, H, H, 2, 2, 10, 10, 1, 1, 0, 0, 1);   /* :166-172 */
+        lba_add(H, A + li * (LD + 1), 3, 3, 10, LD);                          /* H_LL :176-183 */
+        lba_add(H + 3, B + pi + li * SH, 6, 3, 10, SH);                       /* H_PL :185-192 */
+        lba_add(H + 9, B + (li + 1) * SH - 1, 1, 3, 10, SH);                  /* H_Lf :194-201 */
+        lba_add(H + 33, C + pi * (SH + 1), 6, 6, 10, SH);                     /* H_PP :203-210 */
+        lba_add(H + 39, C + (pi + 1) * SH - 1, 1, 6, 10, SH);                 /* H_Pf :212-219 */
+      }
+    }
+    for (int I = 0; I < LD; I += 3) orc_invert_3x3(A + I * LD + I, LD);        /* :227 */
+    orc_matmul2(LD, PD, LD, A, B, BA, BA, LD, SH, SH, SH, 1, 1, 0, 0, 0);      /* :230-235 */
+    orc_matmul2(PD, PD, LD, B, BA, C, C, SH, SH, SH, SH, -1, 1, 1, 1, 0);      /* :238-243 */
+  }
+  free(A); free(B); free(BA);
+}
+
+/* ===================================================================== */
 /* Counter-based random numbers shared by the generators and the sampler   */
 /* ===================================================================== */
 

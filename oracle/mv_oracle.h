@@ -73,6 +73,10 @@ void orc_matmul2(size_t I, size_t J, size_t K, const float* A, const float* B,
                  const float* D, float* C, size_t sA, size_t sB, size_t sD, size_t sC,
                  float a_scale, float b_scale, float d_scale, int tA, int tB);
 
+/* ---- local bundle adjustment: Schur complement (src/local_bundle_adjustment.c:133-246) ---- */
+void orc_invert_3x3(float* matrix, int stride);
+void orc_lba_schur(int n_ldmks, int n_poses, int chunk, const float* J, float* C);
+
 /* ---- Gauss-Newton PnP RANSAC (parity unpinned; this repository's definition) ---- */
 typedef struct {
   float fx, fy, cx, cy;

@@ -124,6 +124,8 @@ class Oracle:
         L.orc_projection_error.argtypes = [_f32p, _f32p, _f32p, _f32p, _f32p]
         L.orc_matmul.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, _f32p] + [C.c_size_t] * 3 + [C.c_float] * 2 + [C.c_int] * 2
         L.orc_matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_int] * 2
+        L.orc_invert_3x3.argtypes = [_f32p, C.c_int]
+        L.orc_lba_schur.argtypes = [C.c_int, C.c_int, C.c_int, _f32p, _f32p]
         L.orc_pnp_gn.argtypes = [C.POINTER(PnpCfg), C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, _f32p, _f32p, C.c_void_p]
         L.orc_synth_frame.argtypes = [C.POINTER(SynthCfg), C.c_int, C.c_int, C.c_int, _i8p, _i8p, _f32p]
         L.orc_track_pair.argtypes = [C.POINTER(TrackCfg), C.c_int, _i8p, _i8p, _f32p, _i8p, _i8p, C.POINTER(PairResult)]
@@ -200,6 +202,20 @@ class Oracle:
                             None if hyp is None else hyp.ctypes.data)
         return pose, stats, hyp
 
+    def lba_schur(self, J, chunk=4):
+        """J float32 [n_ldmks, n_poses, 20] -> C float32 [(6P+1), (6P+1)] (column-major storage)."""
+        J = np.ascontiguousarray(J, np.float32)
+        n_l, n_p, _ = J.shape
+        sh = 6 * n_p + 1
+        out = np.zeros((sh, sh), np.float32)
+        self.lib.orc_lba_schur(n_l, n_p, chunk, J.reshape(-1), out.reshape(-1))
+        return out
+
+    def invert_3x3(self, m, stride=3):
+        m = np.ascontiguousarray(m, np.float32).copy()
+        self.lib.orc_invert_3x3(m.reshape(-1), stride)
+        return m
+
     def synth_frame(self, seed, rows, cols, frame, off_x, off_y, keypoint_permille=140, noise_amp=6):
         cfg = SynthCfg(seed, rows, cols, keypoint_permille, noise_amp)
         cells = rows * cols
@@ -247,6 +263,9 @@ class Reference:
         L.svd.argtypes = [C.c_float] * 9 + [C.POINTER(C.c_float)] * 27
         L.ref_run_nms.restype = C.c_int
         L.ref_run_nms.argtypes = [_i32p, C.POINTER(C.c_int), _i32p]
+        L.ref_lba_run.restype = C.c_int
+        L.ref_lba_run.argtypes = [C.c_void_p, _f32p]
+        L.ref_invert_3x3.argtypes = [_f32p, C.c_int]
         L.matmul.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, _f32p] + [C.c_size_t] * 3 + [C.c_float] * 2 + [C.c_bool] * 2
         L.matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_bool] * 2
 
@@ -272,6 +291,20 @@ class Reference:
         n = self.lib.ref_run_tracking(p1, p2, C.byref(ni), inl, E)
         return dict(n=n, pts0=p1[:n].copy(), pts1=p2[:n].copy(), num_inliers=ni.value,
                     inliers=inl[:ni.value].copy(), best_E=E)
+
+    def lba_run(self, flat=None):
+        """local_bundle_adjustment.c's main() as shipped; `flat` (640 floats, the 64 x 10
+        column-major factor matrix of a chunk) replaces its i*10+j input.  Returns C [49, 49]."""
+        out = np.zeros((49, 49), np.float32)
+        f = None if flat is None else np.ascontiguousarray(flat, np.float32)
+        dim = self.lib.ref_lba_run(None if f is None else f.ctypes.data, out.reshape(-1))
+        assert dim == 49
+        return out
+
+    def invert_3x3(self, m, stride=3):
+        m = np.ascontiguousarray(m, np.float32).copy()
+        self.lib.ref_invert_3x3(m.reshape(-1), stride)
+        return m
 
     def run_nms(self, semi_scale1, semi1):
         """Runs the reference's run_nms main() (src/run_nms.c:42-175) on this frame (its image1).
@@ -302,3 +335,22 @@ class Reference:
         self.lib.svd(*[float(v) for v in A.reshape(-1)], *[C.byref(o) for o in outs])
         vals = np.array([o.value for o in outs], np.float32)
         return vals[:9].reshape(3, 3), vals[9:18].reshape(3, 3), vals[18:].reshape(3, 3)
+
+
+def lba_reference_factors(flat=None, n_ldmks=1000, n_poses=8, chunk=4):
+    """The factor blocks main() of local_bundle_adjustment.c actually uses, as the [n_ldmks, n_poses, 20]
+    input of the parametrised forms: every chunk re-creates the same 64 x 10 column-major matrix
+    (:92-98, i*10+j unless `flat` replaces it) and factor (chunk_i, pose) is the 20 floats at row
+    pose * chunk_i of its [32][20] view (:157, the index is a product in the reference)."""
+    if flat is None:
+        flat = np.zeros(640, np.float32)
+        for j in range(10):
+            for i in range(64):
+                flat[j * 64 + i] = i * 10 + j
+    flat = np.asarray(flat, np.float32)
+    J = np.zeros((n_ldmks, n_poses, 20), np.float32)
+    for l in range(n_ldmks):
+        ci = l % chunk
+        for p in range(n_poses):
+            J[l, p] = flat[20 * (p * ci):20 * (p * ci) + 20]
+    return J

@@ -137,3 +137,33 @@ int ref_run_nms(int* events, int* n_events, int* keypoints) {
  * instantiate them here so tests can call the originals. */
 #include "gemmini_functions_cpu.h"
 #include "local_feature_pool.h"
+
+/* local_bundle_adjustment.c runs as shipped (its main() renamed).  It hands its result, the reduced
+ * camera matrix C, to cholesky() -- a stub in the reference (:88-90) that only prints; that symbol is
+ * weakened in the object (oracle/Makefile) so this definition receives the matrix instead. */
+static float g_lba_C[64 * 64];
+static int g_lba_dim;
+void cholesky(float* matrix, int dim, int stride) {
+  (void)stride;
+  g_lba_dim = dim;
+  if (dim <= 64) memcpy(g_lba_C, matrix, sizeof(float) * (size_t)dim * (size_t)dim);
+}
+/* The program's input generator (:92-98, i*10+j) is weakened the same way: with `J` given, every
+ * chunk's 64 x 10 column-major factor matrix is filled from it instead, so the reference's loop
+ * can be observed on inputs that do not end in NaN. */
+static const float* g_lba_J;
+void initialize_random_matrix(float* matrix, int rows, int cols) {
+  for (int j = 0; j < cols; j++)
+    for (int i = 0; i < rows; i++) matrix[j * rows + i] = g_lba_J ? g_lba_J[j * rows + i] : (float)(i * 10 + j);
+}
+int ref_lba_main(void);
+void invert_3x3(float* matrix, int stride);   /* local_bundle_adjustment.c:48-75 */
+int ref_lba_run(const float* J, float* C) {
+  g_lba_dim = 0;
+  g_lba_J = J;
+  ref_lba_main();
+  g_lba_J = 0;
+  if (C) memcpy(C, g_lba_C, sizeof(float) * (size_t)g_lba_dim * (size_t)g_lba_dim);
+  return g_lba_dim;
+}
+void ref_invert_3x3(float* matrix, int stride) { invert_3x3(matrix, stride); }

@@ -1,0 +1,123 @@
+"""Local bundle adjustment, Schur complement of the landmarks (src/local_bundle_adjustment.c:133-246,
+SURVEY §8f rank 4).
+
+  T1  the reference program itself (oracle/_ref): its main() on its own input -- whose result is NaN
+      in all 48 x 48 pose entries, the 3 x 3 landmark blocks it builds being singular -- and on
+      substituted inputs that stay finite; the matrix it passes to cholesky() is the answer.
+  T2  the parametrised restatement (oracle/mv_oracle.c) == T1 bit for bit, == the golden file.
+  GPU mv_lba_schur_batch == T2 / the golden file bit for bit (NaNs compared as NaNs).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from oracle import orc
+
+
+def same_bits(a, b):
+    a = np.ascontiguousarray(a, np.float32)
+    b = np.ascontiguousarray(b, np.float32)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and (na == nb).all() and (a[~na].view(np.int32) == b[~nb].view(np.int32)).all()
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return dict(np.load(os.path.join(GOLDEN, "ref_lba.npz")))
+
+
+def _flat(golden, k):
+    return None if k == 0 else golden["flat"][k]
+
+
+def test_oracle_equals_golden(oracle, golden):
+    for k in range(golden["C"].shape[0]):
+        J = orc.lba_reference_factors(_flat(golden, k))
+        assert same_bits(oracle.lba_schur(J, 4), golden["C"][k]), k
+    # the reference's own input: every pose entry NaN, the gradient row finite
+    c0 = golden["C"][0]
+    assert np.isnan(c0[:48, :48]).all() and np.isfinite(c0[:48, 48]).all() and (c0[48] == 0).all()
+    for m, inv in zip(golden["inv_in"], golden["inv_out"]):
+        assert oracle.invert_3x3(m).tobytes() == inv.tobytes()
+
+
+def test_oracle_equals_reference(oracle, reference):
+    rng = np.random.default_rng(7)
+    for k in range(6):
+        flat = None if k == 0 else (rng.normal(size=640) * (1.0 if k < 4 else 100.0)).astype(np.float32)
+        assert same_bits(oracle.lba_schur(orc.lba_reference_factors(flat), 4), reference.lba_run(flat)), k
+    for _ in range(100):
+        m = rng.normal(size=(3, 3)).astype(np.float32)
+        assert oracle.invert_3x3(m).tobytes() == reference.invert_3x3(m).tobytes()
+
+
+def test_oracle_solves_a_real_window(oracle):
+    """With Jacobians of full rank the restatement is the textbook reduced camera system:
+    C = H_PP - H_PL H_LL^-1 H_LP and the gradient row g_P - H_PL H_LL^-1 g_L (float64 check)."""
+    rng = np.random.default_rng(3)
+    L, P = 40, 3
+    J = rng.normal(size=(L, P, 20)).astype(np.float32)
+    C = oracle.lba_schur(J, 4).astype(np.float64)
+    Hpp = np.zeros((6 * P + 1, 6 * P + 1))
+    S = np.zeros((6 * P + 1, 6 * P + 1))
+    for l in range(L):
+        Hll = np.zeros((3, 3)); Hpl = np.zeros((6 * P + 1, 3))
+        for p in range(P):
+            Jf = J[l, p].astype(np.float64).reshape(10, 2).T       # 2 x 10
+            H = Jf.T @ Jf
+            Hll += H[:3, :3]
+            Hpl[6 * p:6 * p + 6] += H[3:9, :3]
+            Hpl[6 * P] += H[9, :3]
+            Hpp[6 * p:6 * p + 6, 6 * p:6 * p + 6] += H[3:9, 3:9]
+            Hpp[6 * P, 6 * p:6 * p + 6] += H[9, 3:9]
+        S += Hpl @ np.linalg.inv(Hll) @ Hpl.T
+    want = Hpp.copy()
+    want[:6 * P, :6 * P] -= S[:6 * P, :6 * P]
+    got = C.T                                                      # column-major storage
+    scale = np.abs(want).max()
+    assert np.abs(got[:6 * P, :6 * P] - want[:6 * P, :6 * P]).max() < 2e-3 * scale
+    assert np.abs(got[6 * P, :6 * P] - want[6 * P, :6 * P]).max() < 1e-4 * scale   # gradient row: no Schur term
+
+
+# --------------------------------------------------------------------------------------- GPU
+@pytest.mark.gpu
+def test_gpu_equals_golden_and_oracle(tracker, oracle, golden):
+    import torch
+    # the reference's shape (1000 landmarks, 8 poses, chunks of 4), its own input and substituted ones
+    J = np.stack([orc.lba_reference_factors(_flat(golden, k)) for k in range(golden["C"].shape[0])])
+    C = tracker.lba_schur(torch.from_numpy(J).to(tracker.device), 4).cpu().numpy()
+    for k in range(J.shape[0]):
+        assert same_bits(C[k], golden["C"][k]), k
+    # general factors, other shapes (ragged against the thread count), incl. huge and zero entries
+    rng = np.random.default_rng(11)
+    for (L, P, ch, amp) in [(1000, 8, 4, 1.0), (12, 1, 4, 1.0), (64, 3, 2, 1.0), (96, 16, 8, 1.0), (40, 8, 1, 1.0),
+                            (48, 5, 16, 1.0), (200, 8, 4, 1e18), (200, 8, 4, 0.0)]:
+        Jb = (rng.normal(size=(3, L, P, 20)) * amp).astype(np.float32)
+        got = tracker.lba_schur(torch.from_numpy(Jb).to(tracker.device), ch).cpu().numpy()
+        for w in range(3):
+            assert same_bits(got[w], oracle.lba_schur(Jb[w], ch)), (L, P, ch, amp, w)
+
+
+@pytest.mark.gpu
+def test_gpu_window_is_independent_of_the_batch(tracker):
+    """Full size: 296 windows of 1000 landmarks x 8 poses in one launch; each equals its own launch."""
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(5)
+    J = torch.randn((296, 1000, 8, 20), generator=g).to(tracker.device)
+    C = tracker.lba_schur(J, 4)
+    assert torch.isfinite(C).all()
+    for w in (0, 147, 295):
+        one = tracker.lba_schur(J[w:w + 1].contiguous(), 4)
+        assert one.cpu().numpy().tobytes() == C[w:w + 1].cpu().numpy().tobytes()
+    again = tracker.lba_schur(J, 4)
+    assert again.cpu().numpy().tobytes() == C.cpu().numpy().tobytes()
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_bad_shapes(tracker):
+    import torch
+    J = torch.zeros((1, 10, 2, 20), device=tracker.device)
+    with pytest.raises(Exception):
+        tracker.lba_schur(J, 4)          # 10 landmarks are not a multiple of 4
