@@ -13,9 +13,10 @@
 // Bit-identical to the reference program on its own input and on substituted inputs
 // (tests/test_lba.py, oracle/ref_harness.c).
 //
-// Bound: HBM.  A window reads 80 B per factor (640 KB for 1000 landmarks x 8 poses) and writes
-// (6P+1)^2 floats; the arithmetic is ~150 flop per factor-byte-free entry and latency-bound per
-// CTA (dependent additions), so throughput comes from the number of resident windows.
+// Bound: FP32 issue.  A window reads 80 B per factor (640 KB for 1000 landmarks x 8 poses) and
+// writes (6P+1)^2 floats, against 21.9 MFLOP of multiplies and adds that must be rounded one by one
+// (no FMA, the reference has none): 34 flop/B, above the ridge of the non-fused rate (37 TFLOP/s /
+// 6.5 TB/s = 5.7).  tools/lba_bench.py measures both.
 #include "mv_common.cuh"
 
 namespace {
@@ -154,6 +155,158 @@ lba_schur_kernel(int n_ldmks, int n_poses, int chunk, const float* __restrict__ 
   for (int e = tid; e < SH * SH; e += kLbaThreads) out[e] = C[e];
 }
 
+// The reference's shape (8 poses, chunks of 4) with everything a compile-time constant: the 48 x 48
+// pose block of C never leaves registers -- 256 threads, one 3 x 3 tile each for the whole window,
+// so a k-step of the update costs 6 shared loads for 9 multiply-adds -- and the index arithmetic of
+// the scatter folds away.  Same sums in the same order as the generic kernel above.
+constexpr int kP8 = 8, kC4 = 4;
+__global__ void __launch_bounds__(256)
+lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __restrict__ C_all) {
+  constexpr int P = kP8, CH = kC4, PD = 6 * P, SH = PD + 1, LD = 3 * CH, NF = CH * P;
+  __shared__ __align__(16) float Jc[NF * 20];
+  __shared__ float Hs[NF * 100];
+  __shared__ float A[LD * LD], Ai[LD * LD];
+  __shared__ float B[SH * LD];
+  __shared__ float BA[SH * LD];
+  __shared__ float Crow[PD];            // last row of C (pose gradient), column-major row SH-1
+  const int tid = threadIdx.x;
+  const int ti = tid >> 4, tj = tid & 15;           // tile: rows 3ti.., columns 3tj.. of C[i*SH + j]
+  const float* J = J_all + (size_t)blockIdx.x * n_ldmks * P * 20;
+
+  float c[3][3];
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) c[a][b] = 0.0f;
+  for (int e = tid; e < LD * LD; e += 256) { A[e] = 0.0f; Ai[e] = 0.0f; }
+  for (int e = tid; e < SH * LD; e += 256) BA[e] = 0.0f;
+  if (tid < PD) Crow[tid] = 0.0f;
+  float hprev = 0.0f;
+  const bool diag = (ti >> 1) == (tj >> 1);         // the tile lies in a pose's 6 x 6 diagonal block
+  const int pose = ti >> 1, di = 3 * (ti & 1), dj = 3 * (tj & 1);
+
+  for (int c0 = 0; c0 < n_ldmks; c0 += CH) {
+    // ---- phase 0
+    {
+      const float4* src = reinterpret_cast<const float4*>(J + (size_t)c0 * P * 20);
+      if (tid < NF * 5) reinterpret_cast<float4*>(Jc)[tid] = __ldg(src + tid);
+      if (tid < CH * 9) {
+        const int I = (tid / 9) * 3, i = (tid % 9) / 3, j = tid % 3;
+        A[(I + i) * LD + I + j] = 0.0f;
+      }
+      for (int e = tid; e < SH * LD; e += 256) B[e] = 0.0f;
+    }
+    __syncthreads();
+    // ---- phase 1: factor products
+    if (tid < 100) {
+      const int i = tid / 10, j = tid % 10;
+#pragma unroll 4
+      for (int f = 0; f < NF; f++) {
+        const float* Jf = Jc + f * 20;
+        float h = __fmul_rn(0.0f, hprev);
+        h = __fadd_rn(h, __fmul_rn(Jf[i * 2], Jf[j * 2]));
+        h = __fadd_rn(h, __fmul_rn(Jf[i * 2 + 1], Jf[j * 2 + 1]));
+        Hs[f * 100 + tid] = h;
+        hprev = h;
+      }
+    }
+    __syncthreads();
+    // ---- phase 2: scatter into A, B and the gradient rows (the pose blocks are added in phase 5)
+    {
+      constexpr int nA = CH * 9, nB = NF * 18, nBf = CH * 3, nCf = P * 6;
+      for (int e = tid; e < nA + nB + nBf + nCf; e += 256) {
+        if (e < nA) {
+          const int ci = e / 9, j = (e % 9) / 3, i = e % 3, li = ci * 3;
+          float v = A[(li + j) * LD + li + i];
+#pragma unroll
+          for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + i], v);
+          A[(li + j) * LD + li + i] = v;
+        } else if (e < nA + nB) {
+          const int q = e - nA, f = q / 18, j = (q % 18) / 6, i = q % 6;
+          const int ci = f / P, p = f % P;
+          float* b = B + p * 6 + i + (ci * 3 + j) * SH;
+          *b = __fadd_rn(Hs[f * 100 + j * 10 + 3 + i], *b);
+        } else if (e < nA + nB + nBf) {
+          const int q = e - nA - nB, ci = q / 3, j = q % 3;
+          float* b = B + (ci * 3 + j) * SH + SH - 1;
+          float v = *b;
+#pragma unroll
+          for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + 9], v);
+          *b = v;
+        } else {
+          const int q = e - nA - nB - nBf, p = q / 6, j = q % 6;
+          float v = Crow[p * 6 + j];
+#pragma unroll
+          for (int ci = 0; ci < CH; ci++) v = __fadd_rn(Hs[(ci * P + p) * 100 + (3 + j) * 10 + 9], v);
+          Crow[p * 6 + j] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- phase 3: A^-1 into Ai; one thread per entry of a block's inverse (each recomputes the
+    // determinant: same operations, same value).  Ai's off-diagonal blocks stay 0 like A's.
+    if (tid < CH * 9) {
+      const int blk = tid / 9, ent = tid % 9;
+      const float* M = A + (blk * 3) * LD + blk * 3;
+      float m[9];
+#pragma unroll
+      for (int j = 0; j < 3; j++)
+#pragma unroll
+        for (int i = 0; i < 3; i++) m[j * 3 + i] = M[j * LD + i];
+      const float det = __fadd_rn(__fsub_rn(__fmul_rn(m[0], __fsub_rn(__fmul_rn(m[4], m[8]), __fmul_rn(m[5], m[7]))),
+                                            __fmul_rn(m[1], __fsub_rn(__fmul_rn(m[3], m[8]), __fmul_rn(m[5], m[6])))),
+                                  __fmul_rn(m[2], __fsub_rn(__fmul_rn(m[3], m[7]), __fmul_rn(m[4], m[6]))));
+      // cofactor `ent` of local_bundle_adjustment.c:60-68: (m[p]*m[q] - m[r]*m[s]) / det, its four
+      // operands read by index (entry e of the 3 x 3 copy is M[(e/3)*LD + e%3])
+      const int sh = 4 * (8 - ent);   // tables packed one hex digit per entry, entry 0 first
+      const int cp = (int)((0x421502310ull >> sh) & 15), cq = (int)((0x875683764ull >> sh) & 15);
+      const int cr = (int)((0x512320401ull >> sh) & 15), cs = (int)((0x784865673ull >> sh) & 15);
+      const float vp = M[(cp / 3) * LD + cp % 3], vq = M[(cq / 3) * LD + cq % 3];
+      const float vr = M[(cr / 3) * LD + cr % 3], vs = M[(cs / 3) * LD + cs % 3];
+      Ai[(blk * 3 + ent / 3) * LD + blk * 3 + ent % 3] = __fdiv_rn(__fsub_rn(__fmul_rn(vp, vq), __fmul_rn(vr, vs)), det);
+    }
+    __syncthreads();
+    // ---- phase 4: B A^-1
+    for (int e = tid; e < LD * PD; e += 256) {
+      const int i = e / PD, j = e % PD;
+      float v = __fmul_rn(0.0f, BA[i * SH + j]);
+#pragma unroll
+      for (int k = 0; k < LD; k++) v = __fadd_rn(v, __fmul_rn(Ai[i * LD + k], B[k * SH + j]));
+      BA[i * SH + j] = v;
+    }
+    __syncthreads();
+    // ---- phase 5: this chunk's H_PP terms (diagonal tiles, landmark by landmark), then C -= B A^-1 B^T
+    if (diag) {
+#pragma unroll
+      for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+          // C[i*SH + j], i = 6 pose + di + a, j = 6 pose + dj + b  <-  H[(3 + di + a)*10 + 3 + dj + b]
+          float v = c[a][b];
+#pragma unroll
+          for (int ci = 0; ci < CH; ci++) v = __fadd_rn(Hs[(ci * P + pose) * 100 + (3 + di + a) * 10 + 3 + dj + b], v);
+          c[a][b] = v;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < LD; k++) {
+      const float b0 = -B[k * SH + 3 * ti], b1 = -B[k * SH + 3 * ti + 1], b2 = -B[k * SH + 3 * ti + 2];
+      const float a0 = BA[k * SH + 3 * tj], a1 = BA[k * SH + 3 * tj + 1], a2 = BA[k * SH + 3 * tj + 2];
+      c[0][0] = __fadd_rn(c[0][0], __fmul_rn(b0, a0)); c[0][1] = __fadd_rn(c[0][1], __fmul_rn(b0, a1)); c[0][2] = __fadd_rn(c[0][2], __fmul_rn(b0, a2));
+      c[1][0] = __fadd_rn(c[1][0], __fmul_rn(b1, a0)); c[1][1] = __fadd_rn(c[1][1], __fmul_rn(b1, a1)); c[1][2] = __fadd_rn(c[1][2], __fmul_rn(b1, a2));
+      c[2][0] = __fadd_rn(c[2][0], __fmul_rn(b2, a0)); c[2][1] = __fadd_rn(c[2][1], __fmul_rn(b2, a1)); c[2][2] = __fadd_rn(c[2][2], __fmul_rn(b2, a2));
+    }
+    __syncthreads();
+  }
+  float* out = C_all + (size_t)blockIdx.x * SH * SH;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int b = 0; b < 3; b++) out[(3 * ti + a) * SH + 3 * tj + b] = c[a][b];
+  if (tid < PD) out[tid * SH + SH - 1] = Crow[tid];
+  if (tid < SH) out[PD * SH + tid] = 0.0f;          // the last column stays 0, as in the reference
+}
+
 }  // namespace
 
 extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
@@ -169,7 +322,11 @@ extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks,
   if (smem > 48 * 1024)
     MV_CUDA(ctx, cudaFuncSetAttribute(lba_schur_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mv_prof_scope ps(ctx, "lba");
-  lba_schur_kernel<<<n_windows, kLbaThreads, smem, ctx->stream>>>(n_ldmks, n_poses, chunk, d_J, d_C);
+  const bool generic = getenv("MV_LBA_GENERIC") && atoi(getenv("MV_LBA_GENERIC"));   // A/B knob
+  if (n_poses == kP8 && chunk == kC4 && !generic)
+    lba_schur_p8c4_kernel<<<n_windows, 256, 0, ctx->stream>>>(n_ldmks, d_J, d_C);
+  else
+    lba_schur_kernel<<<n_windows, kLbaThreads, smem, ctx->stream>>>(n_ldmks, n_poses, chunk, d_J, d_C);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }
