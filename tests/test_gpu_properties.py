@@ -216,3 +216,65 @@ def test_trajectory_chain_is_associative(tracker, tk):
     t = second[:, :, 3] + first[-1, :, 3]
     assert np.abs(whole[cut:, :, :3] - R).max() < 1e-11
     assert np.abs(whole[cut:, :, 3] - t).max() < 1e-9 * max(1.0, np.abs(t).max())
+
+
+# ------------------------------------------------------------------ edge cases of the whole path
+def _oracle_seq(oracle, orc, synth, hs, hd, hz, rows, cols, N, M, mv, H):
+    cfg = orc.TrackCfg(orc.MatchCfg(rows, cols, 4, 4, 4, M, 0.9, 0.2), orc.pnp_cfg(hypotheses=H, seed=0, lanes=1),
+                       N, mv, 10, 1.1, float(synth.SEMI_SCALE))
+    return [oracle.track_pair(cfg, p, hs[p], hd[p], hz[p], hs[p + 1], hd[p + 1]) for p in range(hs.shape[0] - 1)]
+
+
+def test_sequence_with_empty_and_degenerate_frames(tracker, tk, oracle, synth):
+    """A sequence whose frames 2 and 3 have no keypoint at all (every logit negative), whose frame 5
+    has every descriptor saturated at -128 (maximal wrap-around of the score products) and whose
+    frame 7 has all-zero descriptors (the zero-norm rule of squared_dist): pairs without queries,
+    without candidates and without matches return the identity pose and zero counts, everything
+    else equals the oracle; the host-buffer path returns the same bytes."""
+    import torch
+    from oracle import orc
+    rows, cols, n_frames, seed = 24, 80, 9, 2
+    N, M, mv, H = 100, 150, 1000, 64
+    off = synth.default_offsets(n_frames, seed)
+    semi, desc, depth = tracker.synth_frames(seed, rows, cols, 0, off)
+    semi[2:4] = -5
+    desc[5] = -128
+    desc[7] = 0
+    scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+    p = tk.track_params(rows, cols, top_n=N, max_valid=mv, max_matches=M, hypotheses=H)
+    res = tk.results_to_numpy(tracker.track_sequence(p, semi, scale, desc, depth))
+    hs, hd, hz = semi.cpu().numpy(), desc.cpu().numpy(), depth.cpu().numpy()
+    ref = _oracle_seq(oracle, orc, synth, hs, hd, hz, rows, cols, N, M, mv, H)
+    for pi, r in enumerate(ref):
+        got = res[pi]
+        assert got["status"] == 0
+        assert got["num_matches"] == r.num_matches, pi
+        assert got["ransac_inliers"] == r.ransac_inliers, pi
+        assert got["pnp_inliers"] == r.pnp_inliers, pi
+        assert np.allclose(got["q"], list(r.q), atol=1e-5) and np.allclose(got["t"], list(r.t), atol=1e-4), pi
+    # pairs (1,2): no candidates; (2,3): neither; (3,4): no queries... all without a match
+    for pi in (1, 2, 3):
+        assert res[pi]["num_matches"] == 0 and res[pi]["pnp_inliers"] == 0
+        assert list(res[pi]["q"]) == [1, 0, 0, 0] and list(res[pi]["t"]) == [0, 0, 0]
+    assert res[0]["num_matches"] > 0
+    host, _, _ = tracker.track_sequence_host(p, hs, np.full(n_frames, synth.SEMI_SCALE, np.float32), hd, hz)
+    assert host.tobytes() == res.tobytes()
+
+
+def test_two_frame_sequence_and_single_pair_batches(tracker, tk, oracle, synth):
+    """The smallest sequence (one pair) through both entry points, at the KITTI grid."""
+    import torch
+    from oracle import orc
+    rows, cols, seed = 47, 155, 9
+    N, M, mv, H = 1000, 1024, 8192, 32
+    off = synth.default_offsets(2, seed)
+    semi, desc, depth = tracker.synth_frames(seed, rows, cols, 0, off)
+    scale = torch.full((2,), float(synth.SEMI_SCALE), device=tracker.device)
+    p = tk.track_params(rows, cols, top_n=N, max_valid=mv, max_matches=M, hypotheses=H)
+    res = tk.results_to_numpy(tracker.track_sequence(p, semi, scale, desc, depth))
+    hs, hd, hz = semi.cpu().numpy(), desc.cpu().numpy(), depth.cpu().numpy()
+    r = _oracle_seq(oracle, orc, synth, hs, hd, hz, rows, cols, N, M, mv, H)[0]
+    assert res.shape == (1,) and res[0]["num_matches"] == r.num_matches > 100
+    assert res[0]["pnp_inliers"] == r.pnp_inliers
+    host, up, down = tracker.track_sequence_host(p, hs, np.full(2, synth.SEMI_SCALE, np.float32), hd, hz)
+    assert host.tobytes() == res.tobytes() and down == 64
