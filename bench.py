@@ -132,7 +132,35 @@ def cpu_port_throughput(budget_s: float, n_threads: int | None = None):
     rounds = int(max(1, min(budget_s / per_round, (N_FRAMES - 1) // cores)))
     n = min(N_FRAMES - 1, cores * rounds)
     secs, out = o.bench_sequence(cfg, syn, offs[:n + 1], 0, n, cores)
+    cpu_port_throughput.last_results = out      # the checker's records of pairs [0, n)
     return n / secs, cores, n, secs
+
+
+def parity_against_port(resn, out, n):
+    """The timed GPU records of the first n pairs against the CPU port's, in the same run: counts and
+    the selected hypothesis exactly, the pose within BASELINE.json's tolerance (1e-5 rad / 1e-5)."""
+    bad = 0
+    max_ang = max_dt = 0.0
+    for p in range(n):
+        r, g = out[p], resn[p]
+        exact = (g["num_matches"] == r.num_matches and g["ransac_inliers"] == r.ransac_inliers
+                 and g["pnp_inliers"] == r.pnp_inliers and g["best_hypothesis"] == r.best_h and g["status"] == r.status)
+        q1 = np.asarray(g["q"], np.float64); q2 = np.asarray(list(r.q), np.float64)
+        q1 = q1 / np.linalg.norm(q1); q2 = q2 / np.linalg.norm(q2)
+        # angle of the relative rotation from the vector part of q1 * conj(q2) (well conditioned near zero)
+        vx = q1[0] * q2[1] - q1[1] * q2[0] - q1[2] * q2[3] + q1[3] * q2[2]
+        vy = q1[0] * q2[2] + q1[1] * q2[3] - q1[2] * q2[0] - q1[3] * q2[1]
+        vz = q1[0] * q2[3] - q1[1] * q2[2] + q1[2] * q2[1] - q1[3] * q2[0]
+        ang = 2.0 * float(np.arctan2(np.sqrt(vx * vx + vy * vy + vz * vz), abs(float(np.dot(q1, q2)))))
+        t2 = np.asarray(list(r.t), np.float64)
+        dt = float(np.linalg.norm(np.asarray(g["t"], np.float64) - t2) / max(1.0, np.linalg.norm(t2)))
+        if r.num_matches > 0:
+            max_ang, max_dt = max(max_ang, ang), max(max_dt, dt)
+        if not exact or ang > 1e-5 or dt > 1e-5:
+            bad += 1
+    return {"pairs_checked": int(n), "mismatches": int(bad), "max_rotation_error_rad": max_ang,
+            "max_translation_error_rel": max_dt,
+            "what": "num_matches, ransac_inliers, pnp_inliers, best hypothesis exact; pose within 1e-5 rad / 1e-5"}
 
 
 def run_reference(args, rank: int):
@@ -397,7 +425,8 @@ def main():
         v, cores, n, secs = cpu_port_throughput(budget_s=15.0)
         cpu = {"value": v, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                "sample": f"first {n} pairs of the same sequence, {secs:.1f} s, OpenMP over pairs, "
-                         "oracle/mv_oracle.c -O3 -march=native"}
+                         "oracle/mv_oracle.c -O3 -march=native",
+               "parity": parity_against_port(resn, cpu_port_throughput.last_results, n)}
 
     if rank == 0:
         line = {
