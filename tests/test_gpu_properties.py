@@ -72,6 +72,14 @@ def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
             got[form] = (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes())
     for form in ("nosort", "mask", "dense"):
         assert got[form] == got["sorted"], form
+    # ... and the sorted kernel with 128 or 256 hypotheses per CTA (chosen by launch size otherwise)
+    for gpw in ("1", "2"):
+        os.environ["MV_PNP_GPW"] = gpw
+        try:
+            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
+        finally:
+            del os.environ["MV_PNP_GPW"]
+        assert (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes()) == got["sorted"], gpw
 
 
 def test_pnp_hypothesis_does_not_depend_on_hypothesis_count(tracker, synth):
