@@ -50,3 +50,28 @@ def test_reference_driver_runs_on_the_library():
     if not os.path.exists(DROPIN_BIN):
         pytest.skip("oracle/_ref/tracking_main_dropin not built")
     assert _lines(DROPIN_BIN) == _golden()
+
+
+LBA_BIN = os.path.join(ROOT, "oracle", "_ref", "lba_dropin")
+
+
+@pytest.mark.gpu
+def test_reference_lba_driver_runs_its_matmul_shim_on_the_library():
+    """src/local_bundle_adjustment.c, unmodified, compiled against this repository's
+    include/gemmini_functions_cpu.h (declarations only): its 8 500 matmul2 calls execute in
+    libmaveric_b200.so on the GPU and the matrix it hands to cholesky() is the one the all-reference
+    run produces (tests/golden/ref_lba.npz, case 0: NaN in the pose block, finite gradient row)."""
+    import numpy as np
+    if not os.path.exists(LBA_BIN):
+        pytest.skip("oracle/_ref/lba_dropin not built")
+    nm = subprocess.run(["nm", "-D", "--undefined-only", LBA_BIN], capture_output=True, text=True).stdout
+    assert re.search(r"\bU matmul2\b", nm)
+    out = subprocess.run([LBA_BIN], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.split()
+    assert lines[:2] == ["dim", "49"]
+    got = np.array([int(x, 16) for x in lines[2:]], np.uint32).view(np.float32).reshape(49, 49)
+    want = np.load(os.path.join(GOLDEN, "ref_lba.npz"))["C"][0]
+    nan = np.isnan(want)
+    assert (np.isnan(got) == nan).all()
+    assert (got[~nan].view(np.int32) == want[~nan].view(np.int32)).all()
