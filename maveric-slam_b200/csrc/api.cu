@@ -918,7 +918,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     if (after) MV_CUDA(c, cudaStreamWaitEvent(gs, after, 0));
     mark("gat_beg", k, gs);
     // An SM's L1/shared split is per-SM state: a kernel that asks for no shared memory
-    // configures "all L1", and the PnP CTAs (7 x 31 KB shared) then cannot join that SM until
+    // configures "all L1", and the PnP CTAs (5 x 37 KB shared) then cannot join that SM until
     // it drains.  Ask for the max-shared carveout so both kernels agree on the split.
     static bool carveout_set = false;
     if (!carveout_set) {
