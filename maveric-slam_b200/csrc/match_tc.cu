@@ -47,8 +47,8 @@ constexpr int kBStages = 6;
 constexpr int kBStageBytes = 256 * 64;
 constexpr int kAStages = 2;
 constexpr int kAStageBytes = kTileQ * 64;
-constexpr int kAccStages = 2;
-constexpr int kAccCols = 256;
+constexpr int kMaxAccStages = 16;   // accumulator stages: 512 TMEM columns / columns per chunk (TcGeom)
+constexpr int kTmemCols = 512;
 constexpr int kQueryWarps = 4;
 constexpr int kQueryThreads = 32 * kQueryWarps;     // == kTileQ: one thread per query row
 constexpr int kEpiWarp0 = 2 + kQueryWarps;
@@ -60,6 +60,8 @@ struct TcGeom {
   int rows, cols, cells, shift_x, shift_y, radius, top_n;
   int cx;             // cell columns per chunk
   int n_chunk;        // UMMA N: cx*rows rounded up to 16
+  int acc_stride;     // TMEM columns per accumulator stage: n_chunk rounded up to 32
+  int acc_stages;     // kTmemCols / acc_stride, at most kMaxAccStages
   int vwords;         // validity words per frame (incl. padding)
   int tiles_per_pair, n_items;
   float accept_gt;    // (double)s > thr^2  <=>  s > accept_gt
@@ -173,7 +175,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 
   __shared__ uint64_t bar_full_b[kBStages], bar_empty_b[kBStages];
   __shared__ uint64_t bar_full_a[kAStages], bar_empty_a[kAStages];
-  __shared__ uint64_t bar_acc_full[kAccStages], bar_acc_empty[kAccStages];
+  __shared__ uint64_t bar_acc_full[kMaxAccStages], bar_acc_empty[kMaxAccStages];
   __shared__ uint32_t s_tmem_base;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -184,12 +186,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       mbar_init(smem_u32(&bar_full_a[i]), kQueryThreads);
       mbar_init(smem_u32(&bar_empty_a[i]), 1 + kEpiWarps);
     }
-    for (int i = 0; i < kAccStages; i++) { mbar_init(smem_u32(&bar_acc_full[i]), 1); mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps); }
+    for (int i = 0; i < g.acc_stages; i++) { mbar_init(smem_u32(&bar_acc_full[i]), 1); mbar_init(smem_u32(&bar_acc_empty[i]), kEpiWarps); }
     mbar_fence_init();
     tma_prefetch_desc(&tmap);
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(&s_tmem_base), kAccStages * kAccCols);
+    tmem_alloc(smem_u32(&s_tmem_base), kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -226,12 +228,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         const uint32_t a_addr = smem_u32(sA + a * kAStageBytes);
         for (int c = 0; c < t.n_chunks; c++, chunk++) {
           const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
-          const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
+          const uint32_t acc = chunk % (uint32_t)g.acc_stages, accph = (chunk / (uint32_t)g.acc_stages) & 1;
           mbar_wait(smem_u32(&bar_acc_empty[acc]), accph ^ 1, abort_flag, 3, 64);
           mbar_wait(smem_u32(&bar_full_b[s]), ph, abort_flag, 4);
           tc_fence_after();
           const uint32_t b_addr = smem_u32(sB + s * kBStageBytes);
-          const uint32_t d_addr = tmem_base + acc * kAccCols;
+          const uint32_t d_addr = tmem_base + acc * (uint32_t)g.acc_stride;
           umma_s8(d_addr, umma_desc_k_sw64(a_addr), umma_desc_k_sw64(b_addr), idesc, 0);
           umma_s8(d_addr, umma_desc_k_sw64(a_addr + 32), umma_desc_k_sw64(b_addr + 32), idesc, 1);
           umma_commit(smem_u32(&bar_empty_b[s]));
@@ -412,7 +414,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(13, cp0);
 #endif
       for (int c = 0; c < t.n_chunks; c++, chunk++) {
-        const uint32_t acc = chunk % kAccStages, accph = (chunk / kAccStages) & 1;
+        const uint32_t acc = chunk % (uint32_t)g.acc_stages, accph = (chunk / (uint32_t)g.acc_stages) & 1;
 #ifdef MV_TC_TRACE
         const long long cw0 = clock64();
 #endif
@@ -434,7 +436,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         int col = (wc_lo & ~63) + half * 32;
         if (col + 32 <= wc_lo) col += 64;
         int x0b = chunk_x0 + col / g.rows, y0b = col - (col / g.rows) * g.rows;   // cell coords of column `col`
-        const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * kAccCols;
+        const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)g.acc_stride;
         for (; col < wc_hi; col += 64) {
           const int cb = chunk_cell + col;
           // validity of the block's 32 cells (uniform), minus the padding columns
@@ -529,7 +531,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, kAccStages * kAccCols);
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 #ifdef MV_TC_TRACE
   if (threadIdx.x == 0) {
     const unsigned long long done = atomicAdd(&mv_tc_trace[15], 1ull) + 1;
@@ -564,8 +566,14 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   g.rows = p->rows; g.cols = p->cols; g.cells = p->rows * p->cols;
   g.shift_x = p->shift_x; g.shift_y = p->shift_y; g.radius = p->radius; g.top_n = top_n;
   g.cx = 256 / p->rows;
+  if (const char* e = getenv("MV_TC_CX")) {   // cell columns per chunk (A/B knob; any value gives the same bytes)
+    const int v = atoi(e);
+    if (v >= 1 && v * p->rows <= 256) g.cx = v;
+  }
   if (g.cx > p->cols) g.cx = p->cols;
   g.n_chunk = (g.cx * p->rows + 15) & ~15;
+  g.acc_stride = (g.n_chunk + 31) & ~31;
+  g.acc_stages = kTmemCols / g.acc_stride < kMaxAccStages ? kTmemCols / g.acc_stride : kMaxAccStages;
   g.vwords = (g.cells + 31) / 32 + kVPadWords + (g.cx * p->rows + 31) / 32;
   g.tiles_per_pair = (top_n + kTileQ - 1) / kTileQ;
   g.n_items = n_pairs * g.tiles_per_pair;
