@@ -52,7 +52,8 @@ constexpr int kTmemCols = 512;
 constexpr int kQueryWarps = 4;
 constexpr int kQueryThreads = 32 * kQueryWarps;     // == kTileQ: one thread per query row
 constexpr int kEpiWarp0 = 2 + kQueryWarps;
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;
+constexpr int kParts = kEpiWarps / 4;   // threads per query row, each takes every kParts-th 32-column block
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr int kVPadWords = 12;   // zero words after a frame's validity bits (chunk overrun + funnel)
 
@@ -371,7 +372,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
     // ------------------------------------------------------------ epilogue
     const int ew = warp - kEpiWarp0;
     const int qd = warp & 3;          // TMEM lane quadrant this warp may read
-    const int half = ew >> 2;         // which of the row's two threads
+    const int half = ew >> 2;         // which of the row's kParts threads
     const int row = qd * 32 + lane;
     uint32_t chunk = 0, tile = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
@@ -432,12 +433,12 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         // columns of this chunk some window of the warp can touch: [wc_lo, wc_hi)
         const int wc_lo = max(0, (wx_lo - chunk_x0) * g.rows);
         const int wc_hi = min(col_limit, (wx_hi - chunk_x0 + 1) * g.rows);
-        // this thread's blocks: half, half+2, ... restricted to that range
-        int col = (wc_lo & ~63) + half * 32;
-        if (col + 32 <= wc_lo) col += 64;
+        // this thread's blocks: half, half+kParts, ... restricted to that range
+        int col = (wc_lo / (32 * kParts)) * (32 * kParts) + half * 32;
+        if (col + 32 <= wc_lo) col += 32 * kParts;
         int x0b = chunk_x0 + col / g.rows, y0b = col - (col / g.rows) * g.rows;   // cell coords of column `col`
         const uint32_t t_row = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)g.acc_stride;
-        for (; col < wc_hi; col += 64) {
+        for (; col < wc_hi; col += 32 * kParts) {
           const int cb = chunk_cell + col;
           // validity of the block's 32 cells (uniform), minus the padding columns
           const int o = cb - base_bit;
@@ -494,7 +495,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
               }
             }
           }
-          y0b += 64;
+          y0b += 32 * kParts;
           while (y0b >= g.rows) { y0b -= g.rows; x0b++; }
         }
         tc_fence_before();
@@ -509,13 +510,16 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 #ifdef MV_TC_TRACE
       const long long cm0 = clock64();
 #endif
-      MergeSlot* mslot = sM + (tile & 1) * kTileQ + row;
-      if (half == 1) { mslot->s = bs; mslot->cell = bcell; }
+      MergeSlot* mslot = sM + ((tile & 1) * kTileQ + row) * (kParts - 1);
+      if (half > 0) { mslot[half - 1].s = bs; mslot[half - 1].cell = bcell; }
       asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
       if (half == 0 && active) {
-        const float os = mslot->s;
-        const int oc = mslot->cell;
-        if (oc >= 0 && (bcell < 0 || os > bs || (os == bs && oc < bcell))) { bs = os; bcell = oc; }
+#pragma unroll
+        for (int h = 0; h < kParts - 1; h++) {
+          const float os = mslot[h].s;
+          const int oc = mslot[h].cell;
+          if (oc >= 0 && (bcell < 0 || os > bs || (os == bs && oc < bcell))) { bs = os; bcell = oc; }
+        }
         const size_t out = (size_t)pair * g.top_n + t.q0 + row;
         best_cell[out] = bcell;
         best_score[out] = bs;
@@ -609,7 +613,7 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   }
   const size_t smem = 1024 + (size_t)kBStages * kBStageBytes + (size_t)kAStages * kAStageBytes +
                       sizeof(uint32_t) * (size_t)kAStages * ((g.vwords + 3) & ~3) +
-                      sizeof(RowInfo) * kAStages * kTileQ + sizeof(MergeSlot) * 2 * kTileQ;
+                      sizeof(RowInfo) * kAStages * kTileQ + sizeof(MergeSlot) * 2 * kTileQ * (kParts - 1);
   if (smem > 227 * 1024) MV_BAD_ARG(ctx, "tensor-core matcher: grid too large for the shared-memory validity window");
   MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;
