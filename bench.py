@@ -136,6 +136,53 @@ def cpu_port_throughput(budget_s: float, n_threads: int | None = None):
     return n / secs, cores, n, secs
 
 
+def reference_program_leg(tr, synth, tracking, torch, n_pairs=8192, ref_pairs=128):
+    """What the reference program itself computes (src/tracking_main.c: 24x80 cells, top-100 queries,
+    <= 150 matches, RANSAC-E + pose, no Gauss-Newton PnP): its unmodified sources (oracle/_ref, in process,
+    one core -- it is single-threaded) against the library's batched kernels on this GPU, same inputs."""
+    from oracle import orc
+    if not orc.have_ref():
+        return None
+    rows, cols = 24, 80
+    off = synth.default_offsets(n_pairs + 1, SEED)
+    semi, desc, _ = tr.synth_frames(SEED, rows, cols, 0, off)
+    scale = torch.full((n_pairs + 1,), float(synth.SEMI_SCALE), device=tr.device)
+    mp = tracking.match_params(rows, cols, 4, 4, 4, 150)
+
+    def step():
+        idx, prob, _ = tr.softmax(semi, scale)
+        qp, qi, _, qc, _ = tr.top_n(idx, prob, 100, 1000)
+        pts, cnt, _, _, _ = tr.match(mp, desc, idx, prob, qp, qi, qc)
+        ninl, _, _ = tr.ransac_identity(pts, cnt, 10, 1.1)
+        return pts, cnt, ninl
+
+    for _ in range(3):
+        out = step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        out = step()
+    e1.record()
+    torch.cuda.synchronize()
+    gpu_pairs_s = n_pairs / (e0.elapsed_time(e1) / 5 * 1e-3)
+    pts, cnt, ninl = [x[:ref_pairs].cpu().numpy() for x in out]
+    ref = orc.Reference()
+    hs, hd = semi[:ref_pairs + 1].cpu().numpy(), desc[:ref_pairs + 1].cpu().numpy()
+    t0 = time.perf_counter()
+    res = [ref.tracking_main(synth.SEMI_SCALE, hs[p], hd[p], synth.SEMI_SCALE, hs[p + 1], hd[p + 1])
+           for p in range(ref_pairs)]
+    dt = (time.perf_counter() - t0) / ref_pairs
+    same = all(r["n"] == cnt[p] and r["num_inliers"] == ninl[p]
+               and np.array_equal(r["pts0"], pts[p, :r["n"], :2]) and np.array_equal(r["pts1"], pts[p, :r["n"], 2:])
+               for p, r in enumerate(res))
+    return {"kind": "reference", "cores": 1, "value": 1.0 / dt, "unit": "frame-pairs/s",
+            "workload": "the reference's own program at its native shape: 24x80 cells, N=100, <=150 matches, RANSAC-E + pose "
+                        "(no Gauss-Newton PnP); %d pairs through main() of src/tracking_main.c in process" % ref_pairs,
+            "gpu_same_workload": {"value": gpu_pairs_s, "unit": "frame-pairs/s", "pairs_per_launch": n_pairs},
+            "same_matches_and_inliers": bool(same)}
+
+
 def parity_against_port(resn, out, n):
     """The timed GPU records of the first n pairs against the CPU port's, in the same run: counts and
     the selected hypothesis exactly, the pose within BASELINE.json's tolerance (1e-5 rad / 1e-5)."""
@@ -427,6 +474,10 @@ def main():
                "sample": f"first {n} pairs of the same sequence, {secs:.1f} s, OpenMP over pairs, "
                          "oracle/mv_oracle.c -O3 -march=native",
                "parity": parity_against_port(resn, cpu_port_throughput.last_results, n)}
+        try:
+            cpu["reference_program"] = reference_program_leg(tr, synth, tracking, torch)
+        except Exception as e:   # the main line must not depend on this leg
+            cpu["reference_program"] = {"error": str(e)[:200]}
 
     if rank == 0:
         line = {
