@@ -160,10 +160,10 @@ lba_schur_kernel(int n_ldmks, int n_poses, int chunk, const float* __restrict__ 
 // so a k-step of the update costs 6 shared loads for 9 multiply-adds -- and the index arithmetic of
 // the scatter folds away.  Same sums in the same order as the generic kernel above.
 constexpr int kP8 = 8, kC4 = 4;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __restrict__ C_all) {
   constexpr int P = kP8, CH = kC4, PD = 6 * P, SH = PD + 1, LD = 3 * CH, NF = CH * P;
-  __shared__ __align__(16) float Jc[NF * 20];
+  __shared__ __align__(16) float Jc[2][NF * 20];   // the chunk's factors, next chunk prefetched
   __shared__ float Hs[NF * 100];
   __shared__ float A[LD * LD], Ai[LD * LD];
   __shared__ float B[SH * LD];
@@ -185,51 +185,73 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
   const bool diag = (ti >> 1) == (tj >> 1);         // the tile lies in a pose's 6 x 6 diagonal block
   const int pose = ti >> 1, di = 3 * (ti & 1), dj = 3 * (tj & 1);
 
-  for (int c0 = 0; c0 < n_ldmks; c0 += CH) {
-    // ---- phase 0
-    {
-      const float4* src = reinterpret_cast<const float4*>(J + (size_t)c0 * P * 20);
-      if (tid < NF * 5) reinterpret_cast<float4*>(Jc)[tid] = __ldg(src + tid);
-      if (tid < CH * 9) {
-        const int I = (tid / 9) * 3, i = (tid % 9) / 3, j = tid % 3;
-        A[(I + i) * LD + I + j] = 0.0f;
+  bool serial = false;   // sticky: once a product needed the previous factor's entry, every later one does
+  if (tid < NF * 5) reinterpret_cast<float4*>(Jc[0])[tid] = __ldg(reinterpret_cast<const float4*>(J) + tid);
+  __syncthreads();
+
+  for (int c0 = 0, buf = 0; c0 < n_ldmks; c0 += CH, buf ^= 1) {
+    // ---- phase 1: H = [J|r]^T [J|r] per factor, from the staged factors (2.5 KB per chunk).
+    // The shim computes entry (i, j) of factor f as (0 * h_prev + t0) + t1 with h_prev the same entry of
+    // the previous factor: a serial chain that matters only if h_prev is not finite (the NaN sticks) or
+    // t0 is a zero (whose sign then comes from h_prev).  Fast path: all 256 threads take the 3 200
+    // entries of the chunk with h_prev = +0; if any thread met one of the two cases the chunk -- and
+    // every later one -- is redone by 100 threads walking the factors in order, as the reference does.
+    const float* Jch = Jc[buf];
+    bool special = serial;
+    if (!serial && (tid & 127) < 100) {
+      // entry (i, j) = tid mod 128 (100 of every 128 threads), factors of the thread's parity: all
+      // loads of the 16 factors are independent, so they overlap
+      const int ij = tid & 127, i = ij / 10, j = ij - i * 10;
+      const float* Ji = Jch + (tid >> 7) * 20 + i * 2;
+      const float* Jj = Jch + (tid >> 7) * 20 + j * 2;
+      float* Hd = Hs + (tid >> 7) * 100 + ij;
+#pragma unroll
+      for (int k = 0; k < NF / 2; k++) {
+        const float2 a = *reinterpret_cast<const float2*>(Ji + k * 40);
+        const float2 bb = *reinterpret_cast<const float2*>(Jj + k * 40);
+        const float t0 = __fmul_rn(a.x, bb.x);
+        const float h = __fadd_rn(__fadd_rn(0.0f, t0), __fmul_rn(a.y, bb.y));
+        Hd[k * 200] = h;
+        special = special || t0 == 0.0f || !(fabsf(h) <= 3.402823466e38f);
       }
-      for (int e = tid; e < SH * LD; e += 256) B[e] = 0.0f;
     }
-    __syncthreads();
-    // ---- phase 1: factor products
-    if (tid < 100) {
-      const int i = tid / 10, j = tid % 10;
-#pragma unroll 4
-      for (int f = 0; f < NF; f++) {
-        const float* Jf = Jc + f * 20;
-        float h = __fmul_rn(0.0f, hprev);
-        h = __fadd_rn(h, __fmul_rn(Jf[i * 2], Jf[j * 2]));
-        h = __fadd_rn(h, __fmul_rn(Jf[i * 2 + 1], Jf[j * 2 + 1]));
-        Hs[f * 100 + tid] = h;
-        hprev = h;
+    serial = __syncthreads_or(special) != 0;
+    if (serial) {
+      if (tid < 100) {
+        const int i = tid / 10, j = tid % 10;
+        for (int f = 0; f < NF; f++) {
+          const float* Jf = Jch + f * 20;
+          float h = __fmul_rn(0.0f, hprev);
+          h = __fadd_rn(h, __fmul_rn(Jf[i * 2], Jf[j * 2]));
+          h = __fadd_rn(h, __fmul_rn(Jf[i * 2 + 1], Jf[j * 2 + 1]));
+          Hs[f * 100 + tid] = h;
+          hprev = h;
+        }
       }
+      __syncthreads();
+    } else if (tid < 100) {
+      hprev = Hs[(NF - 1) * 100 + tid];
     }
-    __syncthreads();
     // ---- phase 2: scatter into A, B and the gradient rows (the pose blocks are added in phase 5)
     {
       constexpr int nA = CH * 9, nB = NF * 18, nBf = CH * 3, nCf = P * 6;
       for (int e = tid; e < nA + nB + nBf + nCf; e += 256) {
         if (e < nA) {
+          // (the reference zeroes A's diagonal blocks and B before every chunk, :141-142: the sums
+          // start from +0 here instead of from memory; every entry of B is written below)
           const int ci = e / 9, j = (e % 9) / 3, i = e % 3, li = ci * 3;
-          float v = A[(li + j) * LD + li + i];
+          float v = 0.0f;
 #pragma unroll
           for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + i], v);
           A[(li + j) * LD + li + i] = v;
         } else if (e < nA + nB) {
           const int q = e - nA, f = q / 18, j = (q % 18) / 6, i = q % 6;
           const int ci = f / P, p = f % P;
-          float* b = B + p * 6 + i + (ci * 3 + j) * SH;
-          *b = __fadd_rn(Hs[f * 100 + j * 10 + 3 + i], *b);
+          B[p * 6 + i + (ci * 3 + j) * SH] = __fadd_rn(Hs[f * 100 + j * 10 + 3 + i], 0.0f);
         } else if (e < nA + nB + nBf) {
           const int q = e - nA - nB, ci = q / 3, j = q % 3;
           float* b = B + (ci * 3 + j) * SH + SH - 1;
-          float v = *b;
+          float v = 0.0f;
 #pragma unroll
           for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + 9], v);
           *b = v;
@@ -275,7 +297,10 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
       BA[i * SH + j] = v;
     }
     __syncthreads();
-    // ---- phase 5: this chunk's H_PP terms (diagonal tiles, landmark by landmark), then C -= B A^-1 B^T
+    // ---- phase 5: this chunk's H_PP terms (diagonal tiles, landmark by landmark), then C -= B A^-1 B^T;
+    // the next chunk's factors arrive meanwhile (the barrier that ends the chunk publishes them)
+    if (c0 + CH < n_ldmks && tid < NF * 5)
+      reinterpret_cast<float4*>(Jc[buf ^ 1])[tid] = __ldg(reinterpret_cast<const float4*>(J + (size_t)(c0 + CH) * P * 20) + tid);
     if (diag) {
 #pragma unroll
       for (int a = 0; a < 3; a++)
