@@ -169,7 +169,7 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
                     const int32_t* __restrict__ q_patch, const int32_t* __restrict__ q_idx,
                     const int32_t* __restrict__ q_count,
                     const int32_t* __restrict__ best_cell, const float* __restrict__ best_score,
-                    float* __restrict__ match_pts, int32_t* __restrict__ match_count,
+                    int n_parts, size_t part_stride, float* __restrict__ match_pts, int32_t* __restrict__ match_count,
                     int32_t* __restrict__ match_cell0, int32_t* __restrict__ match_query,
                     float* __restrict__ match_score) {
   __shared__ int s_warp[kEmitThreads / 32];
@@ -183,8 +183,17 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
   __syncthreads();
   for (int i0 = 0; i0 < nq; i0 += kEmitThreads) {
     const int i = i0 + threadIdx.x;
+    // the matcher reports one candidate per part (the tcgen05 kernel: one per epilogue thread of
+    // the query's row); the winner is the larger score, ties to the earlier cell
     int cell = -1;
-    if (i < nq) cell = best_cell[(size_t)pair * top_n + i];
+    float score = 0.0f;
+    if (i < nq) {
+      for (int part = 0; part < n_parts; part++) {
+        const int oc = best_cell[part * part_stride + (size_t)pair * top_n + i];
+        const float os = best_score[part * part_stride + (size_t)pair * top_n + i];
+        if (oc >= 0 && (cell < 0 || os > score || (os == score && oc < cell))) { score = os; cell = oc; }
+      }
+    }
     const unsigned votes = __ballot_sync(0xffffffffu, cell >= 0);
     if (lane == 0) s_warp[wid] = __popc(votes);
     __syncthreads();
@@ -206,7 +215,7 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
       reinterpret_cast<float4*>(match_pts)[o] = v;
       if (match_cell0) match_cell0[o] = cell;
       if (match_query) match_query[o] = i;
-      if (match_score) match_score[o] = best_score[(size_t)pair * top_n + i];
+      if (match_score) match_score[o] = score;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -232,6 +241,7 @@ extern "C" void mv_match_params_default(mv_match_params* p, int rows, int cols) 
   p->use_tensor_cores = 2;                         // auto: tcgen05 tile kernel where its shape limits hold
 }
 
+int mv_match_tc_parts();
 mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs, int top_n,
                              const int32_t* d_f0, const int32_t* d_f1, const int8_t* d_desc,
                              const int32_t* d_max_idx, const float* d_prob, const int32_t* d_q_patch,
@@ -251,17 +261,19 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
   if ((reinterpret_cast<uintptr_t>(d_desc) & 15) || (reinterpret_cast<uintptr_t>(d_match_pts) & 15))
     MV_BAD_ARG(ctx, "mv_match_batch: d_desc and d_match_pts must be 16-byte aligned");
   const int cells = p->rows * p->cols;
+  int use_tc = p->use_tensor_cores;
+  if (use_tc == 2) use_tc = (p->rows <= 256 && n_frames > 0 && p->match_threshold * p->match_threshold >= 0.0) ? 1 : 0;
+  const int n_parts = use_tc ? mv_match_tc_parts() : 1;
+  const size_t part_stride = (size_t)n_pairs * top_n;
   void* bc = nullptr; void* bsc = nullptr;
-  mv_status st = mv_scratch(ctx, "match.best_cell", sizeof(int32_t) * (size_t)n_pairs * top_n, &bc);
+  mv_status st = mv_scratch(ctx, "match.best_cell", sizeof(int32_t) * part_stride * n_parts, &bc);
   if (st) return st;
-  st = mv_scratch(ctx, "match.best_score", sizeof(float) * (size_t)n_pairs * top_n, &bsc);
+  st = mv_scratch(ctx, "match.best_score", sizeof(float) * part_stride * n_parts, &bsc);
   if (st) return st;
 
   // 0: dp4a warp-per-query kernel; 1: tcgen05 tile kernel (error if the shape is outside its
   // limits); 2: the tcgen05 kernel when rows <= 256 and the threshold is a number, else dp4a.
   // Both produce the same bytes (tests/test_gpu_parity.py); tools/match_sweep.py times them.
-  int use_tc = p->use_tensor_cores;
-  if (use_tc == 2) use_tc = (p->rows <= 256 && n_frames > 0 && p->match_threshold * p->match_threshold >= 0.0) ? 1 : 0;
   if (use_tc) {
     st = mv_match_tc_launch(ctx, p, n_frames, n_pairs, top_n, d_f0, d_f1, d_desc, d_max_idx, d_prob,
                             d_q_patch, d_q_count, (int32_t*)bc, (float*)bsc);
@@ -282,7 +294,7 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
     mv_prof_scope ps(ctx, "emit");
     emit_matches_kernel<<<n_pairs, kEmitThreads, 0, ctx->stream>>>(
         p->rows, cells, top_n, p->max_matches, d_f0, d_f1, d_max_idx, d_q_patch, d_q_idx, d_q_count,
-        (const int32_t*)bc, (const float*)bsc, d_match_pts, d_match_count, d_match_cell0, d_match_query,
+        (const int32_t*)bc, (const float*)bsc, n_parts, part_stride, d_match_pts, d_match_count, d_match_cell0, d_match_query,
         d_match_score);
     MV_CHECK_LAUNCH(ctx);
   }

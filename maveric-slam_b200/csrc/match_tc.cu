@@ -164,7 +164,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
                 const int32_t* __restrict__ f1_of, const int8_t* __restrict__ desc,
                 const uint32_t* __restrict__ vbits, const int32_t* __restrict__ q_patch,
                 const int32_t* __restrict__ q_count, int32_t* __restrict__ best_cell,
-                float* __restrict__ best_score, int* abort_flag) {
+                float* __restrict__ best_score, size_t part_stride, int* abort_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
@@ -172,7 +172,6 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
   uint32_t* sV = reinterpret_cast<uint32_t*>(sA + kAStages * kAStageBytes);   // [kAStages][vstride]
   const int vstride = (g.vwords + 3) & ~3;
   RowInfo* sR = reinterpret_cast<RowInfo*>(sV + kAStages * ((g.vwords + 3) & ~3));   // [kAStages][kTileQ]
-  MergeSlot* sM = reinterpret_cast<MergeSlot*>(sR + kAStages * kTileQ);              // [2][kTileQ]
 
   __shared__ uint64_t bar_full_b[kBStages], bar_empty_b[kBStages];
   __shared__ uint64_t bar_full_a[kAStages], bar_empty_a[kAStages];
@@ -506,21 +505,14 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         if (lane == 0) mbar_arrive(smem_u32(&bar_acc_empty[acc]));
       }
 
-      // ---- merge the row's two threads: larger score, ties to the earlier cell
+      // ---- every one of the row's kParts threads reports its own best candidate; the emit kernel
+      // merges them (larger score, ties to the earlier cell).  No barrier between the epilogue warps:
+      // a warp that is done with the tile moves on to the next one.
 #ifdef MV_TC_TRACE
       const long long cm0 = clock64();
 #endif
-      MergeSlot* mslot = sM + ((tile & 1) * kTileQ + row) * (kParts - 1);
-      if (half > 0) { mslot[half - 1].s = bs; mslot[half - 1].cell = bcell; }
-      asm volatile("bar.sync 1, %0;" ::"n"(kEpiWarps * 32) : "memory");
-      if (half == 0 && active) {
-#pragma unroll
-        for (int h = 0; h < kParts - 1; h++) {
-          const float os = mslot[h].s;
-          const int oc = mslot[h].cell;
-          if (oc >= 0 && (bcell < 0 || os > bs || (os == bs && oc < bcell))) { bs = os; bcell = oc; }
-        }
-        const size_t out = (size_t)pair * g.top_n + t.q0 + row;
+      if (active) {
+        const size_t out = (size_t)half * part_stride + (size_t)pair * g.top_n + t.q0 + row;
         best_cell[out] = bcell;
         best_score[out] = bs;
       }
@@ -553,10 +545,13 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 
 }  // namespace
 
+int mv_match_tc_parts() { return kParts; }
+
 mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs, int top_n,
                              const int32_t* d_f0, const int32_t* d_f1, const int8_t* d_desc,
                              const int32_t* d_max_idx, const float* d_prob, const int32_t* d_q_patch,
                              const int32_t* d_q_count, int32_t* d_best_cell, float* d_best_score) {
+  // d_best_cell / d_best_score: [mv_match_tc_parts()][n_pairs][top_n], one candidate per epilogue part
   if (n_frames <= 0) MV_BAD_ARG(ctx, "tensor-core matcher: n_frames must be given");
   if (p->rows > 256) MV_BAD_ARG(ctx, "tensor-core matcher: rows <= 256 (one cell column per TMA box row block)");
   const double thr2 = p->match_threshold * p->match_threshold;
@@ -613,12 +608,12 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   }
   const size_t smem = 1024 + (size_t)kBStages * kBStageBytes + (size_t)kAStages * kAStageBytes +
                       sizeof(uint32_t) * (size_t)kAStages * ((g.vwords + 3) & ~3) +
-                      sizeof(RowInfo) * kAStages * kTileQ + sizeof(MergeSlot) * 2 * kTileQ * (kParts - 1);
+                      sizeof(RowInfo) * kAStages * kTileQ;
   if (smem > 227 * 1024) MV_BAD_ARG(ctx, "tensor-core matcher: grid too large for the shared-memory validity window");
   MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;
   match_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(tmap, g, d_f0, d_f1, d_desc, (const uint32_t*)vb, d_q_patch,
-                                                        d_q_count, d_best_cell, d_best_score, (int*)flag);
+                                                        d_q_count, d_best_cell, d_best_score, (size_t)n_pairs * (size_t)top_n, (int*)flag);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }
