@@ -86,7 +86,7 @@ struct TileSpan {
 };
 
 // Warp-collective: the tile's query count and the cell columns its windows span.
-__device__ __forceinline__ TileSpan tile_span(const TcGeom& g, int item, const int32_t* __restrict__ f0_of,
+__device__ __forceinline__ TileSpan compute_tile_span(const TcGeom& g, int item, const int32_t* __restrict__ f0_of,
                                               const int32_t* __restrict__ f1_of,
                                               const int32_t* __restrict__ q_patch,
                                               const int32_t* __restrict__ q_count) {
@@ -111,6 +111,30 @@ __device__ __forceinline__ TileSpan tile_span(const TcGeom& g, int item, const i
   t.X0 = max(xmin + g.shift_x - g.radius, 0);
   const int X1 = min(xmax + g.shift_x + g.radius, g.cols - 1);
   t.n_chunks = (t.n_rows > 0 && X1 >= t.X0) ? (X1 - t.X0 + g.cx) / g.cx : 0;
+  return t;
+}
+
+// The spans of all tiles, computed once by a small kernel (one warp per tile): every role of the
+// matcher then gets a tile's span with one 16-byte load instead of a chain of dependent loads
+// and shuffles per role and tile.
+__global__ void tile_spans_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restrict__ f1_of,
+                                  const int32_t* __restrict__ q_patch, const int32_t* __restrict__ q_count,
+                                  int4* __restrict__ spans) {
+  const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (item >= g.n_items) return;
+  const TileSpan t = compute_tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+  if ((threadIdx.x & 31) == 0) spans[item] = make_int4(t.n_rows, t.X0, t.n_chunks, 0);
+}
+
+__device__ __forceinline__ TileSpan tile_span(const TcGeom& g, int item, const int32_t* __restrict__ f0_of,
+                                              const int32_t* __restrict__ f1_of, const int4* __restrict__ spans) {
+  TileSpan t;
+  const int pair = item / g.tiles_per_pair;
+  t.q0 = (item - pair * g.tiles_per_pair) * kTileQ;
+  t.f0 = f0_of ? f0_of[pair] : pair;
+  t.f1 = f1_of ? f1_of[pair] : pair + 1;
+  const int4 s = __ldg(spans + item);
+  t.n_rows = s.x; t.X0 = s.y; t.n_chunks = s.z;
   return t;
 }
 
@@ -163,8 +187,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_t* __restrict__ f0_of,
                 const int32_t* __restrict__ f1_of, const int8_t* __restrict__ desc,
                 const uint32_t* __restrict__ vbits, const int32_t* __restrict__ q_patch,
-                const int32_t* __restrict__ q_count, int32_t* __restrict__ best_cell,
-                float* __restrict__ best_score, size_t part_stride, int* abort_flag) {
+                const int32_t* __restrict__ q_count, const int4* __restrict__ spans,
+                int32_t* __restrict__ best_cell, float* __restrict__ best_score, size_t part_stride,
+                int* abort_flag) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;
@@ -204,7 +229,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
     // ------------------------------------------------------------ TMA producer
     uint32_t chunk = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, spans);
       if (lane == 0) {
         for (int c = 0; c < t.n_chunks; c++, chunk++) {
           const uint32_t s = chunk % kBStages, ph = (chunk / kBStages) & 1;
@@ -220,7 +245,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
     const uint32_t idesc = umma_idesc_s8(kTileQ, g.n_chunk);
     uint32_t chunk = 0, tile = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, spans);
       if (t.n_rows == 0) continue;
       if (lane == 0) {
         const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
@@ -250,7 +275,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
     const int row = threadIdx.x - 64;
     uint32_t tile = 0;
     for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, spans);
       if (t.n_rows == 0) continue;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
       mbar_wait(smem_u32(&bar_empty_a[a]), aph ^ 1, abort_flag, 5, 512);
@@ -378,7 +403,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 #ifdef MV_TC_TRACE
       const long long cs0 = clock64();
 #endif
-      const TileSpan t = tile_span(g, item, f0_of, f1_of, q_patch, q_count);
+      const TileSpan t = tile_span(g, item, f0_of, f1_of, spans);
 #ifdef MV_TC_TRACE
       if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(11, cs0);
       const long long cp0 = clock64();
@@ -584,6 +609,9 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   if (st) return st;
   st = mv_scratch(ctx, "match.tc_abort", 256, &flag);
   if (st) return st;
+  void* spans = nullptr;
+  st = mv_scratch(ctx, "match.tc_spans", sizeof(int4) * (size_t)g.n_items, &spans);
+  if (st) return st;
 
   CUtensorMap tmap;
   const cuuint64_t dims[4] = {256, (cuuint64_t)p->rows, (cuuint64_t)p->cols, (cuuint64_t)n_frames};
@@ -606,6 +634,8 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
     valid_bits_kernel<<<grid, 256, 0, ctx->stream>>>(g.cells, g.vwords, g.prob_lt, d_max_idx, d_prob, (uint32_t*)vb);
     MV_CHECK_LAUNCH(ctx);
   }
+  tile_spans_kernel<<<(g.n_items + 7) / 8, 256, 0, ctx->stream>>>(g, d_f0, d_f1, d_q_patch, d_q_count, (int4*)spans);
+  MV_CHECK_LAUNCH(ctx);
   const size_t smem = 1024 + (size_t)kBStages * kBStageBytes + (size_t)kAStages * kAStageBytes +
                       sizeof(uint32_t) * (size_t)kAStages * ((g.vwords + 3) & ~3) +
                       sizeof(RowInfo) * kAStages * kTileQ;
@@ -613,7 +643,7 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;
   match_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(tmap, g, d_f0, d_f1, d_desc, (const uint32_t*)vb, d_q_patch,
-                                                        d_q_count, d_best_cell, d_best_score, (size_t)n_pairs * (size_t)top_n, (int*)flag);
+                                                        d_q_count, (const int4*)spans, d_best_cell, d_best_score, (size_t)n_pairs * (size_t)top_n, (int*)flag);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }
