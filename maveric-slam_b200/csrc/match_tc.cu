@@ -45,7 +45,7 @@ using namespace sm100;
 constexpr int kTileQ = 128;
 constexpr int kBStages = 6;
 constexpr int kBStageBytes = 256 * 64;
-constexpr int kAStages = 2;
+constexpr int kAStages = 4;
 constexpr int kAStageBytes = kTileQ * 64;
 constexpr int kMaxAccStages = 16;   // accumulator stages: 512 TMEM columns / columns per chunk (TcGeom)
 constexpr int kTmemCols = 512;
