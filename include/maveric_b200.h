@@ -302,6 +302,20 @@ mv_status mv_synth_frames(mv_ctx* ctx, const mv_synth_params* p, int first_frame
 mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
                              const float* d_J, float* d_C);
 
+/* The Gauss-Newton step of the reduced camera systems mv_lba_schur_batch returns: S d = -g with S
+ * the 6 n_poses square pose block (only its lower triangle C[j*SH + i], i >= j, is read) and g the
+ * last row.  This is the cholesky(C, ...) call the reference leaves as a stub
+ * (local_bundle_adjustment.c:88-90,247), so the arithmetic is this library's definition (parity
+ * unpinned; stated by oracle/mv_oracle.c:orc_lba_solve): diagonal s + damping * s + 1e-12, L L^T,
+ * two triangular sweeps, every sum an fmaf chain in a fixed order -- the 6 x 6 solve of the PnP
+ * kernel at n = 6 n_poses.
+ *   d_C     float [n_windows][(6 n_poses + 1)^2]   as written by mv_lba_schur_batch
+ *   d_delta float [n_windows][6 n_poses]           the step; 0 where d_ok is 0
+ *   d_ok    int32 [n_windows]                      1 = solved, 0 = a pivot was not positive (NaN included)
+ * n_poses <= 16. */
+mv_status mv_lba_solve_batch(mv_ctx* ctx, int n_windows, int n_poses, float damping,
+                             const float* d_C, float* d_delta, int32_t* d_ok);
+
 #ifdef __cplusplus
 }
 #endif

@@ -332,6 +332,109 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
   if (tid < SH) out[PD * SH + tid] = 0.0f;          // the last column stays 0, as in the reference
 }
 
+// ---------------------------------------------------------------------------------------
+// The step of the reduced camera system, S d = -g: what the reference would get from the
+// cholesky() it leaves as a stub (local_bundle_adjustment.c:88-90,247).  This repository's
+// definition (parity unpinned; the CPU restatement in the test tree states the same sums): the
+// PnP kernel's damped 6 x 6 Cholesky solve at n = 6 n_poses.  One warp owns a window; lane l owns rows
+// l, l+32, l+64 of L (shared memory, row stride n+1 -- odd, so a column is conflict-free and a
+// row element is a broadcast).  Every sum is one thread's fmaf chain in the defined order
+// (k ascending in the factorisation and the forward sweep, descending in the backward sweep),
+// so the parallelism is across rows only and the result is the sequential one bit for bit.
+constexpr int kSolveWarps = 4;
+
+__device__ __forceinline__ float pick3(const float (&v)[3], int slot) {
+  return slot == 0 ? v[0] : (slot == 1 ? v[1] : v[2]);
+}
+
+__global__ void __launch_bounds__(32 * kSolveWarps)
+lba_solve_kernel(int n_windows, int n_poses, float damping, const float* __restrict__ C_all,
+                 float* __restrict__ d_all, int32_t* __restrict__ ok_all) {
+  extern __shared__ __align__(16) float solve_smem[];
+  const int n = 6 * n_poses, SH = n + 1, ST = n + 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int w = blockIdx.x * kSolveWarps + warp;
+  if (w >= n_windows) return;   // whole warps leave; there is no block-wide barrier below
+  const unsigned full = 0xffffffffu;
+  float* L = solve_smem + (size_t)warp * n * ST;
+  const float* C = C_all + (size_t)w * SH * SH;
+  // the lower triangle S[i][j] = C[j*SH + i], i >= j (a column of C is contiguous)
+  for (int j = 0; j < n; j++)
+    for (int i = j + lane; i < n; i += 32) L[i * ST + j] = __ldg(C + (size_t)j * SH + i);
+  __syncwarp();
+
+  float inv[3] = {0.0f, 0.0f, 0.0f}, s[3];
+  bool ok = true;
+  for (int j = 0; j < n; j++) {
+    const float* Lj = L + j * ST;
+    bool act[3];
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int i = lane + 32 * r;
+      act[r] = i < n && i >= j;
+      s[r] = act[r] ? L[i * ST + j] : 0.0f;
+      if (i == j) s[r] = __fadd_rn(__fmaf_rn(damping, s[r], s[r]), 1e-12f);
+    }
+    for (int k = 0; k < j; k++) {
+      const float ljk = Lj[k];
+#pragma unroll
+      for (int r = 0; r < 3; r++)
+        if (act[r]) s[r] = __fmaf_rn(-L[(lane + 32 * r) * ST + k], ljk, s[r]);
+    }
+    const float sj = __shfl_sync(full, pick3(s, j >> 5), j & 31);
+    if (!(sj > 0.0f)) {   // not positive definite (NaN included): uniform across the warp
+      ok = false;
+      break;
+    }
+    const float dj = __fsqrt_rn(sj), ij = __fdiv_rn(1.0f, dj);
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int i = lane + 32 * r;
+      if (i == j) {
+        inv[r] = ij;
+        L[i * ST + j] = dj;
+      } else if (act[r]) {
+        L[i * ST + j] = __fmul_rn(s[r], ij);
+      }
+    }
+    __syncwarp();
+  }
+
+  if (ok) {
+    // L y = -g, column by column: row i meets its terms with k ascending
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const int i = lane + 32 * r;
+      s[r] = i < n ? -__ldg(C + (size_t)i * SH + n) : 0.0f;
+    }
+    for (int k = 0; k < n; k++) {
+      const float yk = __shfl_sync(full, __fmul_rn(pick3(s, k >> 5), pick3(inv, k >> 5)), k & 31);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int i = lane + 32 * r;
+        if (i == k) s[r] = yk;
+        else if (i > k && i < n) s[r] = __fmaf_rn(-L[i * ST + k], yk, s[r]);
+      }
+    }
+    // L^T d = y, column by column from the last: row i meets its terms with k descending
+    for (int k = n - 1; k >= 0; k--) {
+      const float xk = __shfl_sync(full, __fmul_rn(pick3(s, k >> 5), pick3(inv, k >> 5)), k & 31);
+#pragma unroll
+      for (int r = 0; r < 3; r++) {
+        const int i = lane + 32 * r;
+        if (i == k) s[r] = xk;
+        else if (i < k) s[r] = __fmaf_rn(-L[k * ST + i], xk, s[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const int i = lane + 32 * r;
+    if (i < n) d_all[(size_t)w * n + i] = ok ? s[r] : 0.0f;
+  }
+  if (lane == 0) ok_all[w] = ok ? 1 : 0;
+}
+
 }  // namespace
 
 extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
@@ -352,6 +455,22 @@ extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks,
     lba_schur_p8c4_kernel<<<n_windows, 256, 0, ctx->stream>>>(n_ldmks, d_J, d_C);
   else
     lba_schur_kernel<<<n_windows, kLbaThreads, smem, ctx->stream>>>(n_ldmks, n_poses, chunk, d_J, d_C);
+  MV_CHECK_LAUNCH(ctx);
+  return MV_OK;
+}
+
+extern "C" mv_status mv_lba_solve_batch(mv_ctx* ctx, int n_windows, int n_poses, float damping,
+                                        const float* d_C, float* d_delta, int32_t* d_ok) {
+  if (!ctx) return MV_ERR_BAD_ARG;
+  if (n_windows <= 0 || n_poses <= 0 || !d_C || !d_delta || !d_ok) MV_BAD_ARG(ctx, "mv_lba_solve_batch");
+  if (n_poses > 16) MV_BAD_ARG(ctx, "mv_lba_solve_batch: n_poses <= 16");
+  const int n = 6 * n_poses;
+  const size_t smem = sizeof(float) * (size_t)kSolveWarps * n * (n + 1);
+  if (smem > 48 * 1024)
+    MV_CUDA(ctx, cudaFuncSetAttribute(lba_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mv_prof_scope ps(ctx, "lba_solve");
+  lba_solve_kernel<<<(n_windows + kSolveWarps - 1) / kSolveWarps, 32 * kSolveWarps, smem, ctx->stream>>>(
+      n_windows, n_poses, damping, d_C, d_delta, d_ok);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }

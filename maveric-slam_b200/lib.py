@@ -24,6 +24,7 @@ NEW_SYMBOLS = [
     "mv_build_corr_batch", "mv_track_params_default", "mv_track_sequence", "mv_track_sequence_host",
     "mv_chain_transforms", "mv_results_to_transforms", "mv_nms_batch", "run_nms_ex", "mv_synth_frames",
     "mv_lba_schur_batch",
+    "mv_lba_solve_batch",
 ]
 LEGACY_SYMBOLS = [
     "add_Vector2f", "add_Vector3f", "mult_Quaternionf", "create_Quaternionf", "Quaternionf_from_Vector3f",
@@ -103,6 +104,7 @@ def load() -> C.CDLL:
     L.mv_ctx_profile_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i32)]
     L.mv_ctx_pnp_work.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.mv_lba_schur_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    L.mv_lba_solve_batch.argtypes = [vp, i32, i32, C.c_float, vp, vp, vp]
     L.mv_softmax_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]
     L.mv_top_n_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp]
     L.compute_softmax_ex.argtypes = [vp, f32, vp, i32, C.POINTER(i32), vp, vp]

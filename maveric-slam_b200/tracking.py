@@ -380,6 +380,20 @@ class Tracker:
         self.ctx.check(self.lib.mv_lba_schur_batch(self.ctx.h, n_w, n_l, n_p, chunk, self._d(J), self._d(out)))
         return out
 
+    def lba_solve(self, Cm, damping: float = 0.0):
+        """The cholesky() step the reference leaves as a stub (local_bundle_adjustment.c:88-90,247):
+        float32 [n_windows, 6P+1, 6P+1] reduced camera matrices as lba_schur returns them ->
+        (delta float32 [n_windows, 6P], ok int32 [n_windows]); S delta = -g by a damped Cholesky
+        factorisation in a fixed summation order (this library's definition, mv_lba_solve_batch)."""
+        torch = self.torch
+        n_w, sh, _ = Cm.shape
+        n_p = (sh - 1) // 6
+        delta = torch.empty((n_w, 6 * n_p), dtype=torch.float32, device=self.device)
+        ok = torch.empty((n_w,), dtype=torch.int32, device=self.device)
+        self.ctx.check(self.lib.mv_lba_solve_batch(self.ctx.h, n_w, n_p, float(damping), self._d(Cm),
+                                                   self._d(delta), self._d(ok)))
+        return delta, ok
+
     def chain_transforms(self, transforms):
         """python/compute_trajectory.py:49-51,76-77 as a parallel scan: float64 [n, 3, 4] relative
         transforms -> float64 [n+1, 3, 4] frame poses, pose 0 the identity."""

@@ -680,6 +680,52 @@ void orc_lba_schur(int n_ldmks, int n_poses, int chunk, const float* J, float* C
   free(A); free(B); free(BA);
 }
 
+/* The Gauss-Newton step of the reduced camera system: S d = -g with S the pose block of the
+ * matrix orc_lba_schur returns and g its last row.  This is the cholesky() call the reference
+ * leaves as a stub (local_bundle_adjustment.c:88-90,247), so it is THIS REPOSITORY'S DEFINITION
+ * (PARITY UNPINNED): solve6() below, the 6 x 6 solve of the PnP kernel, for n = 6 n_poses --
+ * diagonal s + damping * s + 1e-12, L L^T by rows with k ascending, forward substitution with k
+ * ascending; only the back substitution runs k DESCENDING (n-1 ... i+1), the order in which a
+ * column-oriented sweep meets the terms.  Only the lower triangle S[i][j], i >= j (C[j*SH + i])
+ * is read.  Every sum is a chain of fmaf.  Returns 1 and d, or 0 and d = 0 when a pivot is not
+ * positive (NaN included). */
+int orc_lba_solve(int n_poses, float damping, const float* C, float* d) {
+  const int n = 6 * n_poses, SH = n + 1;
+  float* L = (float*)calloc((size_t)n * n, sizeof(float));
+  float* inv = (float*)calloc((size_t)n, sizeof(float));
+  float* y = (float*)calloc((size_t)n, sizeof(float));
+  int ok = 1;
+  for (int i = 0; i < n; i++) d[i] = 0.0f;
+  for (int j = 0; j < n && ok; j++) {          /* column by column == row by row: same sums */
+    for (int i = j; i < n; i++) {
+      float s = C[(size_t)j * SH + i];
+      if (i == j) s = fmaf(damping, s, s) + 1e-12f;
+      for (int k = 0; k < j; k++) s = fmaf(-L[i * n + k], L[j * n + k], s);
+      if (i == j) {
+        if (!(s > 0.0f)) { ok = 0; break; }
+        L[j * n + j] = sqrtf(s);
+        inv[j] = 1.0f / L[j * n + j];
+      } else {
+        L[i * n + j] = s * inv[j];
+      }
+    }
+  }
+  if (ok) {
+    for (int i = 0; i < n; i++) {
+      float s = -C[(size_t)i * SH + n];
+      for (int k = 0; k < i; k++) s = fmaf(-L[i * n + k], y[k], s);
+      y[i] = s * inv[i];
+    }
+    for (int i = n - 1; i >= 0; i--) {
+      float s = y[i];
+      for (int k = n - 1; k > i; k--) s = fmaf(-L[k * n + i], d[k], s);
+      d[i] = s * inv[i];
+    }
+  }
+  free(L); free(inv); free(y);
+  return ok;
+}
+
 /* ===================================================================== */
 /* Counter-based random numbers shared by the generators and the sampler   */
 /* ===================================================================== */

@@ -76,6 +76,9 @@ void orc_matmul2(size_t I, size_t J, size_t K, const float* A, const float* B,
 /* ---- local bundle adjustment: Schur complement (src/local_bundle_adjustment.c:133-246) ---- */
 void orc_invert_3x3(float* matrix, int stride);
 void orc_lba_schur(int n_ldmks, int n_poses, int chunk, const float* J, float* C);
+/* damped Cholesky step of the reduced camera system (the reference's cholesky() is a stub:
+ * this repository's definition, parity unpinned); 1 = solved, 0 = not positive definite, d = 0 */
+int orc_lba_solve(int n_poses, float damping, const float* C, float* d);
 
 /* ---- Gauss-Newton PnP RANSAC (parity unpinned; this repository's definition) ---- */
 typedef struct {

@@ -126,6 +126,8 @@ class Oracle:
         L.orc_matmul2.argtypes = [C.c_size_t] * 3 + [_f32p, _f32p, C.c_void_p, _f32p] + [C.c_size_t] * 4 + [C.c_float] * 3 + [C.c_int] * 2
         L.orc_invert_3x3.argtypes = [_f32p, C.c_int]
         L.orc_lba_schur.argtypes = [C.c_int, C.c_int, C.c_int, _f32p, _f32p]
+        L.orc_lba_solve.restype = C.c_int
+        L.orc_lba_solve.argtypes = [C.c_int, C.c_float, _f32p, _f32p]
         L.orc_pnp_gn.argtypes = [C.POINTER(PnpCfg), C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, _f32p, _f32p, C.c_void_p]
         L.orc_synth_frame.argtypes = [C.POINTER(SynthCfg), C.c_int, C.c_int, C.c_int, _i8p, _i8p, _f32p]
         L.orc_track_pair.argtypes = [C.POINTER(TrackCfg), C.c_int, _i8p, _i8p, _f32p, _i8p, _i8p, C.POINTER(PairResult)]
@@ -210,6 +212,15 @@ class Oracle:
         out = np.zeros((sh, sh), np.float32)
         self.lib.orc_lba_schur(n_l, n_p, chunk, J.reshape(-1), out.reshape(-1))
         return out
+
+    def lba_solve(self, Cm, damping=0.0):
+        """Cm float32 [(6P+1), (6P+1)] as lba_schur returns it -> (ok, d float32 [6P]): the damped
+        Cholesky step S d = -g (this repository's definition; the reference's cholesky() is a stub)."""
+        Cm = np.ascontiguousarray(Cm, np.float32)
+        n_p = (Cm.shape[0] - 1) // 6
+        d = np.zeros(6 * n_p, np.float32)
+        ok = self.lib.orc_lba_solve(n_p, float(damping), Cm.reshape(-1), d)
+        return int(ok), d
 
     def invert_3x3(self, m, stride=3):
         m = np.ascontiguousarray(m, np.float32).copy()

@@ -158,9 +158,19 @@ void initialize_random_matrix(float* matrix, int rows, int cols) {
 }
 int ref_lba_main(void);
 void invert_3x3(float* matrix, int stride);   /* local_bundle_adjustment.c:48-75 */
+/* The program reads its H_factor (:148) before writing it: 0 * H_factor is the D term of the first
+ * matmul2 (:166-172), so a NaN or Inf left on the stack by whatever ran before would end up in
+ * every sum.  The region its frame will occupy is zeroed first, which makes the run repeatable
+ * and is the reading the restatement states (H starts at 0). */
+static void __attribute__((noinline)) lba_scrub_stack(void) {
+  volatile char pad[1 << 18];
+  memset((void*)pad, 0, sizeof(pad));
+  __asm__ volatile("" : : "r"(pad) : "memory");
+}
 int ref_lba_run(const float* J, float* C) {
   g_lba_dim = 0;
   g_lba_J = J;
+  lba_scrub_stack();
   ref_lba_main();
   g_lba_J = 0;
   if (C) memcpy(C, g_lba_C, sizeof(float) * (size_t)g_lba_dim * (size_t)g_lba_dim);

@@ -6,6 +6,10 @@ SURVEY §8f rank 4).
       substituted inputs that stay finite; the matrix it passes to cholesky() is the answer.
   T2  the parametrised restatement (oracle/mv_oracle.c) == T1 bit for bit, == the golden file.
   GPU mv_lba_schur_batch == T2 / the golden file bit for bit (NaNs compared as NaNs).
+
+The solve of the reduced system (the reference's cholesky() is a stub, :88-90,247) is this
+repository's definition, PARITY UNPINNED: the restatement is checked against a float64 solve and
+the GPU kernel against the restatement bit for bit.
 """
 import os
 
@@ -81,6 +85,55 @@ def test_oracle_solves_a_real_window(oracle):
     assert np.abs(got[6 * P, :6 * P] - want[6 * P, :6 * P]).max() < 1e-4 * scale   # gradient row: no Schur term
 
 
+def _spd_system(rng, P, cond=1.0):
+    """(C as lba_schur lays it out, S, g) for a random SPD pose block."""
+    n = 6 * P
+    A = rng.normal(size=(n + 24, n)) * np.logspace(0, np.log10(cond), n)
+    S = (A.T @ A).astype(np.float32)
+    S = np.tril(S) + np.tril(S, -1).T
+    g = rng.normal(size=n).astype(np.float32)
+    C = np.zeros((n + 1, n + 1), np.float32)
+    C[:n, :n] = S.T                     # [column, row]
+    C[:n, n] = g                        # last row
+    C[n, n] = 3.0
+    return C, S, g
+
+
+def test_oracle_solve_against_float64(oracle):
+    rng = np.random.default_rng(5)
+    for P in (1, 2, 5, 8, 11, 16):
+        C, S, g = _spd_system(rng, P)
+        ok, d = oracle.lba_solve(C, 0.0)
+        want = np.linalg.solve(S.astype(np.float64), -g.astype(np.float64))
+        assert ok == 1 and np.abs(d - want).max() < 1e-4 * np.abs(want).max(), P
+        # only the lower triangle is read
+        C2 = C.copy()
+        iu = np.triu_indices(6 * P, 1)
+        C2[:6 * P, :6 * P].T[iu] = 77.0
+        assert oracle.lba_solve(C2, 0.0)[1].tobytes() == d.tobytes()
+        # damping = Levenberg-Marquardt scaling of the diagonal
+        ok, dd = oracle.lba_solve(C, 0.5)
+        Sd = S.astype(np.float64) + 0.5 * np.diag(np.diag(S).astype(np.float64))
+        want = np.linalg.solve(Sd, -g.astype(np.float64))
+        assert ok == 1 and np.abs(dd - want).max() < 1e-4 * np.abs(want).max(), P
+
+
+def test_oracle_solve_rejects_what_is_not_positive_definite(oracle, golden):
+    rng = np.random.default_rng(6)
+    C, S, g = _spd_system(rng, 3)
+    C[4, 4] = -1.0
+    ok, d = oracle.lba_solve(C, 0.0)
+    assert ok == 0 and not d.any()
+    # the reference's own input: every pose entry is NaN
+    ok, d = oracle.lba_solve(golden["C"][0], 0.0)
+    assert ok == 0 and not d.any()
+    # one pose, 6 x 6: the PnP solve's definition (ascending back substitution differs in order only)
+    C, S, g = _spd_system(rng, 1)
+    ok, d = oracle.lba_solve(C, 1e-3)
+    want = np.linalg.solve(S.astype(np.float64) * (np.eye(6) * 1e-3 + 1), -g.astype(np.float64))
+    assert ok == 1 and np.abs(d - want).max() < 1e-5 * np.abs(want).max()
+
+
 # --------------------------------------------------------------------------------------- GPU
 @pytest.mark.gpu
 def test_gpu_equals_golden_and_oracle(tracker, oracle, golden):
@@ -116,8 +169,65 @@ def test_gpu_window_is_independent_of_the_batch(tracker):
 
 
 @pytest.mark.gpu
+def test_gpu_solve_equals_oracle(tracker, oracle, golden):
+    """mv_lba_solve_batch == the restatement bit for bit: every pose count the library takes, well
+    and badly conditioned systems, damping, and the systems that must be refused."""
+    import torch
+    rng = np.random.default_rng(21)
+    for P in (1, 2, 3, 5, 6, 8, 11, 16):
+        Cs = []
+        for w in range(9):
+            C, _, _ = _spd_system(rng, P, cond=(1.0, 30.0, 1000.0)[w % 3])
+            if w == 4:
+                C[2 * P, 2 * P] = -abs(C[2 * P, 2 * P])          # a negative pivot in the middle
+            if w == 7:
+                C[P, 0] = np.nan
+            Cs.append(C)
+        Cs = np.stack(Cs)
+        for damping in (0.0, 1e-3):
+            d, ok = tracker.lba_solve(torch.from_numpy(Cs).to(tracker.device), damping)
+            d, ok = d.cpu().numpy(), ok.cpu().numpy()
+            for w in range(Cs.shape[0]):
+                ok_o, d_o = oracle.lba_solve(Cs[w], damping)
+                assert ok[w] == ok_o and same_bits(d[w], d_o), (P, w, damping)
+            assert ok[4] == 0 and ok[7] == 0 and ok[0] == 1
+    # Schur complement -> step, end to end on the device at the reference's shape; its own input is refused
+    J = np.stack([orc.lba_reference_factors(_flat(golden, k)) for k in range(golden["C"].shape[0])])
+    Cd = tracker.lba_schur(torch.from_numpy(J).to(tracker.device), 4)
+    d, ok = tracker.lba_solve(Cd, 1e-3)
+    d, ok = d.cpu().numpy(), ok.cpu().numpy()
+    assert ok[0] == 0 and not d[0].any()
+    for k in range(J.shape[0]):
+        ok_o, d_o = oracle.lba_solve(golden["C"][k], 1e-3)
+        assert ok[k] == ok_o and same_bits(d[k], d_o), k
+
+
+@pytest.mark.gpu
+def test_gpu_solve_full_batch_and_residual(tracker):
+    """2 368 windows of 8 poses in one launch: each equals its own launch, and the step solves its
+    system (float64 residual)."""
+    import torch
+    rng = np.random.default_rng(22)
+    base = np.stack([_spd_system(rng, 8)[0] for _ in range(37)])
+    Cs = torch.from_numpy(np.tile(base, (64, 1, 1))).to(tracker.device)
+    d, ok = tracker.lba_solve(Cs, 0.0)
+    assert int(ok.sum()) == Cs.shape[0]
+    dn = d.cpu().numpy()
+    assert dn[:37].tobytes() == dn[37 * 63:].tobytes()
+    for w in (0, 36, 1000, 2367):
+        one, _ = tracker.lba_solve(Cs[w:w + 1].contiguous(), 0.0)
+        assert one.cpu().numpy().tobytes() == dn[w:w + 1].tobytes()
+        S = base[w % 37][:48, :48].T.astype(np.float64)
+        S = np.tril(S) + np.tril(S, -1).T
+        g = base[w % 37][:48, 48].astype(np.float64)
+        assert np.abs(S @ dn[w].astype(np.float64) + g).max() < 1e-3 * np.abs(g).max()
+
+
+@pytest.mark.gpu
 def test_gpu_rejects_bad_shapes(tracker):
     import torch
     J = torch.zeros((1, 10, 2, 20), device=tracker.device)
     with pytest.raises(Exception):
         tracker.lba_schur(J, 4)          # 10 landmarks are not a multiple of 4
+    with pytest.raises(Exception):
+        tracker.lba_solve(torch.zeros((1, 103, 103), device=tracker.device))   # 17 poses

@@ -51,6 +51,17 @@ def main():
     hbm = peaks.get("hbm_gbs", 6650.0)
     ach = (in_bytes + out_bytes) / (ms * 1e-3) / 1e9
 
+    # the step of the reduced systems (mv_lba_solve_batch); C of random factors is SPD
+    for _ in range(3):
+        d, ok = tr.lba_solve(C, 1e-3)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.reps):
+        d, ok = tr.lba_solve(C, 1e-3)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_solve = e0.elapsed_time(e1) / args.reps
+
     o = orc.Oracle()
     Jh = J[:4].cpu().numpy()
     t0 = time.perf_counter()
@@ -77,7 +88,12 @@ def main():
                      "hbm_achieved_gbs": ach, "hbm_peak_gbs": hbm, "algorithmic_bytes": in_bytes + out_bytes},
         "cpu_baseline": {"value": 1.0 / cpu_s, "unit": "windows/s", "cores": 1, "kind": "port",
                          "sample": "%d windows, oracle/mv_oracle.c orc_lba_schur (-O2, the reference's loop order)" % n},
-        "bit_identical_to_cpu": bool(same)}))
+        "bit_identical_to_cpu": bool(same),
+        "solve": {"kernel": "lba_solve_kernel", "ms_per_launch": ms_solve, "windows_solved": int(ok.sum()),
+                  "windows_per_s": args.windows / (ms_solve * 1e-3),
+                  "bit_identical_to_cpu": bool(all(
+                      np.array_equal(o.lba_solve(C[w].cpu().numpy(), 1e-3)[1].view(np.int32),
+                                     d[w].cpu().numpy().view(np.int32)) for w in range(4)))}}))
 
 
 if __name__ == "__main__":
