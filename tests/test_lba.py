@@ -181,7 +181,7 @@ def test_gpu_solve_equals_oracle(tracker, oracle, golden):
             if w == 4:
                 C[2 * P, 2 * P] = -abs(C[2 * P, 2 * P])          # a negative pivot in the middle
             if w == 7:
-                C[P, 0] = np.nan
+                C[0, P] = np.nan                                  # column 0, row P: lower triangle
             Cs.append(C)
         Cs = np.stack(Cs)
         for damping in (0.0, 1e-3):
