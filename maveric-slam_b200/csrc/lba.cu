@@ -165,13 +165,49 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
   constexpr int P = kP8, CH = kC4, PD = 6 * P, SH = PD + 1, LD = 3 * CH, NF = CH * P;
   __shared__ __align__(16) float Jc[2][NF * 20];   // the chunk's factors, next chunk prefetched
   __shared__ float Hs[NF * 100];
-  __shared__ float A[LD * LD], Ai[LD * LD];
-  __shared__ float B[SH * LD];
-  __shared__ float BA[SH * LD];
-  __shared__ float Crow[PD];            // last row of C (pose gradient), column-major row SH-1
+  // A, A^-1, B, B A^-1 and the last row of C (pose gradient, column-major row SH-1) in one array, so
+  // that a destination of the scatter phase is one 16-bit offset
+  constexpr int oA = 0, oAi = LD * LD, oB = 2 * LD * LD, oBA = oB + SH * LD, oCrow = oBA + SH * LD;
+  __shared__ __align__(16) float S[oCrow + PD];
+  float* const A = S + oA; float* const Ai = S + oAi; float* const B = S + oB; float* const BA = S + oBA;
+  float* const Crow = S + oCrow;
+  // scatter phase as a table: entry e sums n entries of Hs (first, stride) onto +0 -- or onto the
+  // destination's old value (the gradient row, which runs on across the chunks) -- and stores the sum
+  constexpr int nA = CH * 9, nB = NF * 18, nBf = CH * 3, nCf = P * 6, nScatter = nA + nB + nBf + nCf;
+  static_assert(CH == 4 && P == 8, "the scatter loop below is written for sums of 1, 4 or 8 terms");
+  __shared__ uint2 tab[nScatter];   // .x = first | dst << 16, .y = n | stride << 8 | accumulate << 31
   const int tid = threadIdx.x;
-  const int ti = tid >> 4, tj = tid & 15;           // tile: rows 3ti.., columns 3tj.. of C[i*SH + j]
+  // Tile of the thread: rows 3ti.., columns 3tj.. of C[i*SH + j].  The 32 tiles inside the poses'
+  // 6 x 6 diagonal blocks (they alone receive the H_PP terms) belong to warp 0, so that only one
+  // warp executes that code; the other 224 tiles follow row by row.
+  int ti, tj;
+  if (tid < 32) {
+    ti = 2 * (tid >> 2) + ((tid >> 1) & 1);
+    tj = 2 * (tid >> 2) + (tid & 1);
+  } else {
+    const int m = tid - 32, r = m % 14;
+    ti = m / 14;
+    tj = r + (r >= 2 * (ti >> 1) ? 2 : 0);
+  }
   const float* J = J_all + (size_t)blockIdx.x * n_ldmks * P * 20;
+  for (int e = tid; e < nScatter; e += 256) {
+    unsigned first, dst, n, stride, acc = 0;
+    if (e < nA) {                      // landmark block: the 8 poses' H_LL entries (:176-183)
+      const int ci = e / 9, j = (e % 9) / 3, i = e % 3, li = ci * 3;
+      first = ci * P * 100 + j * 10 + i; stride = 100; n = P; dst = oA + (li + j) * LD + li + i;
+    } else if (e < nA + nB) {          // pose-landmark block: one H_PL entry each (:185-192)
+      const int q = e - nA, f = q / 18, j = (q % 18) / 6, i = q % 6;
+      const int ci = f / P, p_ = f % P;
+      first = f * 100 + j * 10 + 3 + i; stride = 0; n = 1; dst = oB + p_ * 6 + i + (ci * 3 + j) * SH;
+    } else if (e < nA + nB + nBf) {    // landmark gradient row: the 8 poses' H_Lf entries (:194-201)
+      const int q = e - nA - nB, ci = q / 3, j = q % 3;
+      first = ci * P * 100 + j * 10 + 9; stride = 100; n = P; dst = oB + (ci * 3 + j) * SH + SH - 1;
+    } else {                           // pose gradient row: the chunk's 4 landmarks' H_Pf entries (:212-219)
+      const int q = e - nA - nB - nBf, p_ = q / 6, j = q % 6;
+      first = p_ * 100 + (3 + j) * 10 + 9; stride = P * 100; n = CH; dst = oCrow + p_ * 6 + j; acc = 1;
+    }
+    tab[e] = make_uint2(first | (dst << 16), n | (stride << 8) | (acc << 31));
+  }
 
   float c[3][3];
 #pragma unroll
@@ -182,7 +218,7 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
   for (int e = tid; e < SH * LD; e += 256) BA[e] = 0.0f;
   if (tid < PD) Crow[tid] = 0.0f;
   float hprev = 0.0f;
-  const bool diag = (ti >> 1) == (tj >> 1);         // the tile lies in a pose's 6 x 6 diagonal block
+  const bool diag = tid < 32;                       // the tile lies in a pose's 6 x 6 diagonal block
   const int pose = ti >> 1, di = 3 * (ti & 1), dj = 3 * (tj & 1);
 
   bool serial = false;   // sticky: once a product needed the previous factor's entry, every later one does
@@ -232,37 +268,24 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
     } else if (tid < 100) {
       hprev = Hs[(NF - 1) * 100 + tid];
     }
-    // ---- phase 2: scatter into A, B and the gradient rows (the pose blocks are added in phase 5)
-    {
-      constexpr int nA = CH * 9, nB = NF * 18, nBf = CH * 3, nCf = P * 6;
-      for (int e = tid; e < nA + nB + nBf + nCf; e += 256) {
-        if (e < nA) {
-          // (the reference zeroes A's diagonal blocks and B before every chunk, :141-142: the sums
-          // start from +0 here instead of from memory; every entry of B is written below)
-          const int ci = e / 9, j = (e % 9) / 3, i = e % 3, li = ci * 3;
-          float v = 0.0f;
-#pragma unroll
-          for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + i], v);
-          A[(li + j) * LD + li + i] = v;
-        } else if (e < nA + nB) {
-          const int q = e - nA, f = q / 18, j = (q % 18) / 6, i = q % 6;
-          const int ci = f / P, p = f % P;
-          B[p * 6 + i + (ci * 3 + j) * SH] = __fadd_rn(Hs[f * 100 + j * 10 + 3 + i], 0.0f);
-        } else if (e < nA + nB + nBf) {
-          const int q = e - nA - nB, ci = q / 3, j = q % 3;
-          float* b = B + (ci * 3 + j) * SH + SH - 1;
-          float v = 0.0f;
-#pragma unroll
-          for (int p = 0; p < P; p++) v = __fadd_rn(Hs[(ci * P + p) * 100 + j * 10 + 9], v);
-          *b = v;
-        } else {
-          const int q = e - nA - nB - nBf, p = q / 6, j = q % 6;
-          float v = Crow[p * 6 + j];
-#pragma unroll
-          for (int ci = 0; ci < CH; ci++) v = __fadd_rn(Hs[(ci * P + p) * 100 + (3 + j) * 10 + 9], v);
-          Crow[p * 6 + j] = v;
+    // ---- phase 2: scatter into A, B and the gradient rows (the pose blocks are added in phase 5).
+    // (The reference zeroes A's diagonal blocks and B before every chunk, :141-142: the sums start
+    // from +0 here instead of from memory; every entry of B is written.)
+    for (int e = tid; e < nScatter; e += 256) {
+      const uint2 t = tab[e];
+      const float* src = Hs + (t.x & 0xffffu);
+      float* dst = S + (t.x >> 16);
+      const int n = (int)(t.y & 0xffu), stride = (int)((t.y >> 8) & 0xffffu);
+      float v = (t.y >> 31) ? *dst : 0.0f;
+      v = __fadd_rn(src[0], v);
+      if (n >= CH) {      // n is 1, CH (= 4) or P (= 8)
+        v = __fadd_rn(src[stride], v); v = __fadd_rn(src[2 * stride], v); v = __fadd_rn(src[3 * stride], v);
+        if (n == P) {
+          v = __fadd_rn(src[4 * stride], v); v = __fadd_rn(src[5 * stride], v);
+          v = __fadd_rn(src[6 * stride], v); v = __fadd_rn(src[7 * stride], v);
         }
       }
+      *dst = v;
     }
     __syncthreads();
     // ---- phase 3: A^-1 into Ai; one thread per entry of a block's inverse (each recomputes the
@@ -292,8 +315,11 @@ lba_schur_p8c4_kernel(int n_ldmks, const float* __restrict__ J_all, float* __res
     for (int e = tid; e < LD * PD; e += 256) {
       const int i = e / PD, j = e % PD;
       float v = __fmul_rn(0.0f, BA[i * SH + j]);
+      float ai[LD];   // row i of A^-1: 48 bytes, 16-byte aligned
 #pragma unroll
-      for (int k = 0; k < LD; k++) v = __fadd_rn(v, __fmul_rn(Ai[i * LD + k], B[k * SH + j]));
+      for (int k = 0; k < LD; k += 4) *reinterpret_cast<float4*>(ai + k) = *reinterpret_cast<const float4*>(Ai + i * LD + k);
+#pragma unroll
+      for (int k = 0; k < LD; k++) v = __fadd_rn(v, __fmul_rn(ai[k], B[k * SH + j]));
       BA[i * SH + j] = v;
     }
     __syncthreads();

@@ -154,6 +154,26 @@ def test_gpu_equals_golden_and_oracle(tracker, oracle, golden):
 
 
 @pytest.mark.gpu
+def test_gpu_kernel_forms_return_identical_bytes(tracker, oracle, monkeypatch):
+    """The reference shape has a specialised kernel beside the generic one (MV_LBA_GENERIC): the
+    same sums in the same order, so the same bytes."""
+    import torch
+    rng = np.random.default_rng(12)
+    J = rng.normal(size=(5, 200, 8, 20)).astype(np.float32)
+    J[3, 17] = 0.0                       # zero products: the factor chain of the shim becomes serial
+    J[4, 5, 2, 7] = np.inf
+    Jd = torch.from_numpy(J).to(tracker.device)
+    want = np.stack([oracle.lba_schur(J[w], 4) for w in range(J.shape[0])])
+    for env in ({}, {"MV_LBA_GENERIC": "1"}):
+        monkeypatch.delenv("MV_LBA_GENERIC", raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        got = tracker.lba_schur(Jd, 4).cpu().numpy()
+        for w in range(J.shape[0]):
+            assert same_bits(got[w], want[w]), (env, w)
+
+
+@pytest.mark.gpu
 def test_gpu_window_is_independent_of_the_batch(tracker):
     """Full size: 296 windows of 1000 landmarks x 8 poses in one launch; each equals its own launch."""
     import torch
