@@ -80,6 +80,15 @@ def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
         finally:
             del os.environ["MV_PNP_GPW"]
         assert (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes()) == got["sorted"], gpw
+    # ... and with the re-deal (and its barriers) left out after some or all passes, so that the warps
+    # of a CTA drift apart by whole passes (n = 513 re-stages the correspondences inside every pass)
+    for mask in ("155", "00f", "000"):
+        os.environ["MV_PNP_SORTMASK"] = mask
+        try:
+            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
+        finally:
+            del os.environ["MV_PNP_SORTMASK"]
+        assert (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes()) == got["sorted"], mask
 
 
 def test_pnp_hypothesis_does_not_depend_on_hypothesis_count(tracker, synth):
