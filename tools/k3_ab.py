@@ -1,9 +1,11 @@
 #!/usr/bin/env python
-"""A/B timing of the Gauss-Newton PnP kernel's knobs on the bench workload (4 540 pairs x 1 024
+"""A/B timing of a kernel's environment knobs on the bench workload (4 540 pairs x 1 024
 hypotheses): one process, the knob read per call, CUDA-event kernel times from the context's
-profile mode, results compared byte for byte with the default's.
+profile mode (K3_AB_TAG: pnp by default, or match, detect, ...), results compared byte for byte
+with the default's.
 
     python tools/k3_ab.py [ENV=VALUE[,ENV=VALUE] ...]     e.g.  MV_PNP_SORTMASK=0f MV_PNP_SORTMASK=155
+    K3_AB_TAG=match python tools/k3_ab.py MV_TC_BACKOFF_A=128 MV_TC_BACKOFF_A=128,MV_TC_BACKOFF_ACC=32
 """
 import json
 import os
@@ -17,6 +19,7 @@ import maveric_slam_b200  # noqa: E402,F401
 from maveric_slam_b200 import synth, tracking  # noqa: E402
 
 NF = int(os.environ.get("K3_AB_FRAMES", "4541"))
+TAG = os.environ.get("K3_AB_TAG", "pnp")
 tr = tracking.Tracker(0)
 params = tracking.kitti_track_params(top_n=1000, max_valid=8192, max_matches=1024, hypotheses=1024, refine_iters=10,
                                      sample_iters=4, seed=0, first_pair=0, lanes=1, use_tensor_cores=True)
@@ -38,9 +41,9 @@ for env in variants:
     for _ in range(3):
         res = tr.track_sequence(params, semi, scale, desc, depth)
     tr.ctx.sync()
-    ms = tr.ctx.profile_read("pnp")[0]
+    ms = tr.ctx.profile_read(TAG)[0]
     tr.ctx.profile(False)
     b = res.cpu().numpy().tobytes()
     if ref is None:
         ref = b
-    print(json.dumps({"env": env, "pnp_ms": ms, "same_bytes": b == ref}), flush=True)
+    print(json.dumps({"env": env, TAG + "_ms": ms, "same_bytes": b == ref}), flush=True)
