@@ -67,7 +67,6 @@ struct TcGeom {
   int tiles_per_pair, n_items;
   float accept_gt;    // (double)s > thr^2  <=>  s > accept_gt
   float prob_lt;      // (double)p < min    <=>  p < prob_lt
-  int bo_a, bo_acc;   // epilogue back-off (ns) between polls of a tile's row state / of an accumulator stage
 };
 
 // bit c of frame f's word array: cell c is a candidate (tracking_main.c:142,146)
@@ -315,15 +314,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 #pragma unroll
         for (int c = 0; c < 4; c++) *reinterpret_cast<int4*>(dst + sw64_offset(row, c)) = q4[c];
       }
-#ifdef MV_TC_TRACE
-      const long long cq1 = clock64();
-      if (row == 0) atomicAdd(&mv_tc_trace_q[0], (unsigned long long)(cq1 - cq0));   // spans, validity words, query row staged
-#endif
       asm volatile("bar.sync 2, %0;" ::"n"(kQueryThreads) : "memory");   // validity words visible
-#ifdef MV_TC_TRACE
-      const long long cq2 = clock64();
-      if (row == 0) atomicAdd(&mv_tc_trace_q[1], (unsigned long long)(cq2 - cq1));   // barrier of the four query warps
-#endif
 
       // Leading candidates (tracking_main.c:21-32): every valid window cell, in scan order, is
       // scored over 256 dims until one has a non-zero norm.  The search for the next cell is
@@ -339,9 +330,6 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
         bool searching = x_hi >= x_lo;
         while (true) {
           int c = -1;
-#ifdef MV_TC_TRACE
-          const long long cs_ = clock64();
-#endif
           while (searching && c < 0) {
             c = first_set_in_range(sv, base_bit, slo, sx * g.rows + y_hi);
             if (c < 0) {
@@ -350,10 +338,6 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
               searching = sx <= x_hi;
             }
           }
-#ifdef MV_TC_TRACE
-          const long long ce_ = clock64();
-          if (row == 0) { atomicAdd(&mv_tc_trace_q[3], (unsigned long long)(ce_ - cs_)); atomicAdd(&mv_tc_trace_q[5], 1ull); }
-#endif
           if (!__any_sync(0xffffffffu, c >= 0)) break;
           if (c >= 0) {
             const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)c * 256);
@@ -378,14 +362,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
             slo = c + 1;
             searching = n_cand == 0;   // sticky zero norm: the next valid cell is a leading one too
           }
-#ifdef MV_TC_TRACE
-          __syncwarp();
-          if (row == 0) atomicAdd(&mv_tc_trace_q[4], (unsigned long long)(clock64() - ce_));
-#endif
         }
-#ifdef MV_TC_TRACE
-        if (row == 0) atomicAdd(&mv_tc_trace_q[2], (unsigned long long)(clock64() - cq2));   // search + 256-d evaluation
-#endif
         if (n_cand != 0) {
           const int den_i = (int)((unsigned)n_cand * (unsigned)nq64);
           ri.den_f = __int2float_rn(den_i);
@@ -434,7 +411,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
       if (t.n_rows == 0) continue;
       const int pair = item / g.tiles_per_pair;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
-      mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 6, (unsigned)g.bo_a);
+      mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 6);
       const uint32_t* sv = sV + a * vstride;
       const int base_bit = ((t.X0 * g.rows) >> 5) << 5;
 
@@ -466,7 +443,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
 #ifdef MV_TC_TRACE
         const long long cw0 = clock64();
 #endif
-        mbar_wait(smem_u32(&bar_acc_full[acc]), accph, abort_flag, 7, (unsigned)g.bo_acc);
+        mbar_wait(smem_u32(&bar_acc_full[acc]), accph, abort_flag, 7);
 #ifdef MV_TC_TRACE
         if (ew == 0 && lane == 0) MV_TC_TRACE_ADD(14, cw0);
 #endif
@@ -585,11 +562,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap, TcGeom g, const int32_
              mv_tc_trace[1] * 1e-6, mv_tc_trace[2] * 1e-6, mv_tc_trace[3] * 1e-6, mv_tc_trace[4] * 1e-6, mv_tc_trace[5] * 1e-6 / 128,
              mv_tc_trace[6] * 1e-6 / 256, mv_tc_trace[7] * 1e-6 / 256, mv_tc_trace[8] * 1e-6, mv_tc_trace[9] * 1e-6,
              mv_tc_trace[10] * 1e-6 / 7, mv_tc_trace[11] * 1e-6, mv_tc_trace[12] * 1e-6, mv_tc_trace[13] * 1e-6, mv_tc_trace[14] * 1e-6, g.n_items);
-      printf("tc trace, query warp 2 per tile body (Mcycles): stage-in %.2f barrier %.2f search+lead %.2f (search %.2f, 256-d evaluation %.2f, rounds %llu)\n",
-             mv_tc_trace_q[0] * 1e-6, mv_tc_trace_q[1] * 1e-6, mv_tc_trace_q[2] * 1e-6, mv_tc_trace_q[3] * 1e-6,
-             mv_tc_trace_q[4] * 1e-6, mv_tc_trace_q[5]);
       for (int i = 0; i < 16; i++) mv_tc_trace[i] = 0;
-      for (int i = 0; i < 8; i++) mv_tc_trace_q[i] = 0;
     }
   }
 #endif
@@ -630,9 +603,6 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   g.n_items = n_pairs * g.tiles_per_pair;
   g.accept_gt = mv_round_down(thr2);
   g.prob_lt = mv_round_up(p->min_prob0);
-  g.bo_a = 0; g.bo_acc = 0;
-  if (const char* e = getenv("MV_TC_BACKOFF_A")) g.bo_a = atoi(e);       // A/B knobs
-  if (const char* e = getenv("MV_TC_BACKOFF_ACC")) g.bo_acc = atoi(e);
 
   void* vb = nullptr; void* flag = nullptr;
   mv_status st = mv_scratch(ctx, "match.vbits", sizeof(uint32_t) * (size_t)n_frames * g.vwords, &vb);

@@ -51,7 +51,6 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
 #ifdef MV_TC_TRACE
 // debug build (-DMV_TC_TRACE): cycles spent in every wait site, summed over the grid
 __device__ unsigned long long mv_tc_trace[16];
-__device__ unsigned long long mv_tc_trace_q[8];   // query warps, row 0: segments of a tile's body
 #define MV_TC_TRACE_ADD(who, c0) atomicAdd(&mv_tc_trace[(who)], (unsigned long long)(clock64() - (c0)))
 #else
 #define MV_TC_TRACE_ADD(who, c0)

@@ -5,7 +5,7 @@ profile mode (K3_AB_TAG: pnp by default, or match, detect, ...), results compare
 with the default's.
 
     python tools/k3_ab.py [ENV=VALUE[,ENV=VALUE] ...]     e.g.  MV_PNP_SORTMASK=0f MV_PNP_SORTMASK=155
-    K3_AB_TAG=match python tools/k3_ab.py MV_TC_BACKOFF_A=128 MV_TC_BACKOFF_A=128,MV_TC_BACKOFF_ACC=32
+    K3_AB_TAG=match python tools/k3_ab.py MV_TC_CX=3 MV_TC_CX=2
 """
 import json
 import os
