@@ -279,6 +279,8 @@ extern "C" mv_status mv_match_pair_host(mv_ctx* c, const mv_match_params* p, con
   if (!p || !h_desc0 || !h_desc1 || !max_indices0 || !probs0 || num_queries < 0 || !points1 || !points2 ||
       !num_matches)
     MV_BAD_ARG(c, "mv_match_pair_host");
+  if (p->rows <= 0 || p->cols <= 0 || p->max_matches <= 0)
+    MV_BAD_ARG(c, "mv_match_pair_host: rows, cols and max_matches must be positive");
   const int cells = p->rows * p->cols;
   const int top_n = num_queries > 0 ? num_queries : 1;
   const int M = p->max_matches;
@@ -563,6 +565,12 @@ struct SeqScratch {
   uint8_t* flags;
 };
 
+// sizes every scratch buffer of the sequence calls is computed from
+static bool seq_params_ok(const mv_track_params* p) {
+  return p->match.rows > 0 && p->match.cols > 0 && p->top_n > 0 && p->max_valid > 0 && p->match.max_matches > 0 &&
+         (long long)p->match.rows * p->match.cols <= 0x7fffffffLL;
+}
+
 static mv_status seq_scratch(mv_ctx* c, const mv_track_params* p, int n_frames, const char* ns, SeqScratch* o) {
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
@@ -644,6 +652,7 @@ extern "C" mv_status mv_track_sequence(mv_ctx* c, const mv_track_params* p, int 
   if (!c) return MV_ERR_BAD_ARG;
   if (!p || n_frames < 2 || !d_semi || !d_semi_scale || !d_desc || !d_depth || !d_results)
     MV_BAD_ARG(c, "mv_track_sequence");
+  if (!seq_params_ok(p)) MV_BAD_ARG(c, "mv_track_sequence: rows, cols, top_n, max_valid and max_matches must be positive");
   SeqScratch w;
   mv_status st;
   if ((st = seq_scratch(c, p, n_frames, "seq", &w))) return st;
@@ -787,6 +796,8 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   if (!c) return MV_ERR_BAD_ARG;
   if (!p || n_frames < 2 || !h_semi || !h_semi_scale || !h_desc || !h_depth || !h_results)
     MV_BAD_ARG(c, "mv_track_sequence_host");
+  if (!seq_params_ok(p))
+    MV_BAD_ARG(c, "mv_track_sequence_host: rows, cols, top_n, max_valid and max_matches must be positive");
   const int cells = p->match.rows * p->match.cols;
   const int n_pairs = n_frames - 1;
   // chunk = two full waves of the PnP kernel at its capped residency (5 CTAs/SM, see below); the
@@ -839,12 +850,21 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   }
   if ((st = mv_scratch(c, "host.results", sizeof(mv_pair_result) * (size_t)n_pairs, &dres))) return st;
   if ((st = mv_scratch(c, "host.moved", 16, &dmoved))) return st;
+  // every event of this call lives in `events` and is destroyed on any return path
+  struct EventBag {
+    std::vector<cudaEvent_t> v;
+    ~EventBag() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
+  } events;
+  auto new_event = [&](cudaEvent_t* e) -> mv_status {
+    MV_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+    events.v.push_back(*e);
+    return MV_OK;
+  };
   cudaEvent_t ready[NB], consumed[NB], detected[NB], copied[NB];
   for (int b = 0; b < NB; b++) {
-    MV_CUDA(c, cudaEventCreateWithFlags(&ready[b], cudaEventDisableTiming));
-    MV_CUDA(c, cudaEventCreateWithFlags(&consumed[b], cudaEventDisableTiming));
-    MV_CUDA(c, cudaEventCreateWithFlags(&detected[b], cudaEventDisableTiming));
-    MV_CUDA(c, cudaEventCreateWithFlags(&copied[b], cudaEventDisableTiming));
+    if ((st = new_event(&ready[b])) || (st = new_event(&consumed[b])) || (st = new_event(&detected[b])) ||
+        (st = new_event(&copied[b])))
+      return st;
   }
   // NB chunks in flight on three engines:
   //   copy_stream    DMA of a chunk's logits (and descriptors/depth when not gathering)
@@ -855,7 +875,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   //                  one-warp CTA that fits in them, so it is resident alongside.
   // whatever the caller queued on the compute stream must be ordered before the staging
   cudaEvent_t start;
-  MV_CUDA(c, cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  if ((st = new_event(&start))) return st;
   MV_CUDA(c, cudaEventRecord(start, c->stream));
   MV_CUDA(c, cudaStreamWaitEvent(c->copy_stream, start, 0));
   MV_CUDA(c, cudaStreamWaitEvent(c->gather_stream, start, 0));
@@ -910,7 +930,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   // MV_HOST_EAGER_GATHER=1: start a chunk's row gather as soon as its detector is done (A/B knob)
   const bool eager_gather = getenv("MV_HOST_EAGER_GATHER") && atoi(getenv("MV_HOST_EAGER_GATHER"));
   cudaEvent_t matched;
-  MV_CUDA(c, cudaEventCreateWithFlags(&matched, cudaEventDisableTiming));
+  if ((st = new_event(&matched))) return st;
   auto launch_gather = [&](int k, cudaEvent_t after) -> mv_status {
     const int b = k % NB, p0 = chunk_first(k), nf = chunk_frames(k);
     cudaStream_t gs = c->gather_stream;
@@ -995,11 +1015,6 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   MV_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   MV_CUDA(c, cudaMemcpyAsync(&moved, dmoved, 8, cudaMemcpyDeviceToHost, c->gather_stream));
   MV_CUDA(c, cudaStreamSynchronize(c->gather_stream));
-  for (int i = 0; i < NB; i++) {
-    cudaEventDestroy(ready[i]); cudaEventDestroy(consumed[i]); cudaEventDestroy(detected[i]); cudaEventDestroy(copied[i]);
-  }
-  cudaEventDestroy(start);
-  cudaEventDestroy(matched);
   if (trace) {
     for (auto& m : marks) {
       float ms = 0.f;

@@ -295,3 +295,34 @@ def test_two_frame_sequence_and_single_pair_batches(tracker, tk, oracle, synth):
     assert res[0]["pnp_inliers"] == r.pnp_inliers
     host, up, down = tracker.track_sequence_host(p, hs, np.full(2, synth.SEMI_SCALE, np.float32), hd, hz)
     assert host.tobytes() == res.tobytes() and down == 64
+
+
+def test_sequence_calls_reject_nonpositive_sizes(tracker, tk, synth):
+    """Status codes instead of the reference's undefined behaviour: a non-positive grid, query count or
+    match capacity is MV_ERR_BAD_ARG from both sequence entry points, before anything is allocated."""
+    import torch
+    from maveric_slam_b200 import lib
+    rows, cols = 24, 80
+    off = synth.default_offsets(2, 1)
+    semi, desc, depth = tracker.synth_frames(1, rows, cols, 0, off)
+    scale = torch.full((2,), float(synth.SEMI_SCALE), device=tracker.device)
+    hs, hd, hz = semi.cpu().numpy(), desc.cpu().numpy(), depth.cpu().numpy()
+    hsc = np.full(2, synth.SEMI_SCALE, np.float32)
+
+    def broken(**kw):
+        p = tk.track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=32)
+        for k, v in kw.items():
+            if k in ("rows", "cols", "max_matches"):
+                setattr(p.match, k, v)
+            else:
+                setattr(p, k, v)
+        return p
+
+    for kw in ({"rows": 0}, {"cols": -3}, {"top_n": 0}, {"max_valid": 0}, {"max_matches": 0}):
+        with pytest.raises(lib.MvError, match="bad argument"):
+            tracker.track_sequence(broken(**kw), semi, scale, desc, depth)
+        with pytest.raises(lib.MvError, match="bad argument"):
+            tracker.track_sequence_host(broken(**kw), hs, hsc, hd, hz)
+    # and the context is still usable afterwards
+    res = tk.results_to_numpy(tracker.track_sequence(broken(), semi, scale, desc, depth))
+    assert res.shape == (1,)
