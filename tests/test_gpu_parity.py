@@ -142,6 +142,26 @@ def test_match_zero_descriptors_and_ties(tk, oracle, synth, tc):
 
 
 @pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
+@pytest.mark.parametrize("seed", range(4))
+def test_detector_and_match_on_adversarial_pairs(tk, oracle, synth, seed, tc):
+    """The inputs of test_t2_equals_t1_on_adversarial_descriptors (tests/adversarial.py: wrapping products,
+    exact ties, runs of zero descriptors, sign flips, probability ties at the top-N threshold) -- where
+    the restatement is checked against the reference's own code -- through the library's detector
+    and both matchers: same query lists, matches, candidate cells and score bits."""
+    from adversarial import adversarial_pair
+    scale, s0, d0, s1, d1 = adversarial_pair(oracle, synth, seed)
+    idx, pr, pa, ix, ref = _oracle_pair(oracle, 24, 80, s0, d0, s1, d1, 100, 150, scale=scale, max_valid=1000)
+    gi, gp, _ = tk.compute_softmax(scale, s0)
+    assert (gi == idx).all() and (bits(gp) == bits(pr)).all()
+    ga = tk.compute_top_N(scale, s1, 100, max_valid=1000)
+    assert (ga[0] == pa).all() and (ga[1] == ix).all()
+    got = tk.match_pair(tk.match_params(24, 80, use_tensor_cores=tc), d0, d1, gi, gp, ga[0], ga[1])
+    assert got["n"] == ref["n"] > 0
+    assert (got["cell0"] == ref["cell0"]).all() and (bits(got["score"]) == bits(ref["score"])).all()
+    assert (got["pts0"] == ref["pts0"]).all() and (got["pts1"] == ref["pts1"]).all()
+
+
+@pytest.mark.parametrize("tc", [False, True], ids=["dp4a", "tcgen05"])
 def test_match_self_pair_golden(tk, image0, kat, tc):
     idx, pr, _ = tk.compute_softmax(image0["semi_scale"], image0["semi"], legacy=True)
     pa, ix, _ = tk.compute_top_N(image0["semi_scale"], image0["semi"], 100, legacy=True)

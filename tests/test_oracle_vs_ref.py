@@ -112,6 +112,26 @@ def test_t2_equals_t1_on_native_shape(oracle, reference, synth, seed):
     assert ni == res["num_inliers"] and (inl == res["inliers"]).all()
 
 
+@pytest.mark.parametrize("seed", range(8))
+def test_t2_equals_t1_on_adversarial_descriptors(oracle, reference, synth, seed):
+    """Inputs built to sit on the hazards of SURVEY App. B: descriptors of extreme entries (+-127/-128: both
+    int32 products at tracking_main.c:154 wrap, scores come out negative, > 1, inf or NaN), runs of identical
+    descriptors (exact score ties: the first candidate in x-outer / y-inner order must win), all-zero
+    descriptors at the head of a window (the sticky 256-d branch of squared_dist) and low-entropy logits
+    (probability ties at the top-N threshold)."""
+    from adversarial import adversarial_pair
+    scale, s0, d0, s1, d1 = adversarial_pair(oracle, synth, seed)
+    a = reference.top_n(scale, s1, 100)
+    b = oracle.top_n(scale, s1, 100)
+    assert all((x == y).all() for x, y in zip(a, b[:2])) and (bits(a[2]) == bits(b[2])).all()
+    res = reference.tracking_main(scale, s0, d0, scale, s1, d1)
+    m = _t2_pair(oracle, scale, s0, d0, scale, s1, d1)
+    assert res["n"] == m["n"]
+    assert (res["pts0"] == m["pts0"]).all() and (res["pts1"] == m["pts1"]).all()
+    E, inl, ni, wrote = oracle.ransac_identity(m["pts0"], m["pts1"])
+    assert ni == res["num_inliers"] and (inl == res["inliers"]).all()
+
+
 def test_t2_equals_t1_shuffled_real_descriptors(oracle, reference, image0):
     # real descriptors (int32 wrap territory), frame 1 = frame 0 shifted by the search offset
     semi, desc = image0["semi"], image0["desc"]
