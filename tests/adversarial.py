@@ -41,3 +41,22 @@ def adversarial_pair(oracle, synth, seed):
     live = (ki != 64) & (kp > 0.2)           # keypoint cells only: the valid count stays below top_N.c:91's exit(1)
     s1[live, :64] = np.where(s1[live, :64] > 0, 40, s1[live, :64])
     return scale, s0, d0, s1, d1
+
+
+def adversarial_logits(seed):
+    """-> int8 [1920, 65] detector input for the order-dependent parts of top_N.c (seed in 0..5 picks the
+    value palette): equal maxima inside a cell, logits of 127, dustbin-only and all-negative cells, zero
+    logits, and a few distinct probabilities shared by hundreds of cells."""
+    rng = np.random.default_rng(77 + seed)
+    semi = np.full((1920, 65), -50, np.int8)
+    semi[:, 64] = 60                                        # dustbin wins: not a keypoint
+    active = rng.random(1920) < 0.3                         # ~576 valid cells, below top_N.c:91's exit(1)
+    palette = np.array([[-5, 0, 3, 3, 120, 127], [0, 0, 1, 1, 2, 2], [-128, -1, 0, 127, 127, 127],
+                        [5, 5, 5, 5, 5, 5], [-3, 7, 7, 90, 90, 126], [0, 0, 0, 0, 0, 0]], np.int8)[seed]
+    n_act = int(active.sum())
+    semi[active] = palette[rng.integers(0, 6, size=(n_act, 65))]
+    semi[active, 64] = rng.choice(np.array([-9, 0, 3], np.int8), size=n_act)
+    lone = np.flatnonzero(~active)[:40]
+    semi[lone[:20], :] = -7                                 # all negative
+    semi[lone[20:], :64] = -1                               # dustbin the only non-negative entry
+    return semi

@@ -132,6 +132,26 @@ def test_t2_equals_t1_on_adversarial_descriptors(oracle, reference, synth, seed)
     assert ni == res["num_inliers"] and (inl == res["inliers"]).all()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_t2_equals_t1_on_adversarial_logits(oracle, reference, seed):
+    """Detector inputs on the order-dependent parts of top_N.c: equal maxima inside a cell (the strict `>`
+    at :39 keeps the first), logits of 127 under large scales (the int32 powers of approx_exp at their
+    largest, exponentials up to ~1e9), cells whose only non-negative entry is the dustbin, all-negative
+    cells (denominator FLT_MIN), zero logits, and a few distinct probabilities shared by hundreds of cells
+    (the `prob >= threshold` cut at :116-133 then depends on patch order alone)."""
+    from adversarial import adversarial_logits
+    semi = adversarial_logits(seed)
+    for scale in (0.01, 0.35622698, 1.0, 3.0):
+        i1, p1, n1 = reference.softmax(scale, semi)
+        i2, p2, n2 = oracle.softmax(scale, semi)
+        assert n1 == n2 and (i1 == i2).all() and (bits(p1) == bits(p2)).all()
+        for N in (100, 37, 1):
+            a = reference.top_n(scale, semi, N)
+            b = oracle.top_n(scale, semi, N)
+            assert len(a[0]) == len(b[0]) and b[3] == 0
+            assert all((x == y).all() for x, y in zip(a, b[:2])) and (bits(a[2]) == bits(b[2])).all()
+
+
 def test_t2_equals_t1_shuffled_real_descriptors(oracle, reference, image0):
     # real descriptors (int32 wrap territory), frame 1 = frame 0 shifted by the search offset
     semi, desc = image0["semi"], image0["desc"]
