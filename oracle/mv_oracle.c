@@ -1076,7 +1076,8 @@ void orc_track_pair(const orc_track_cfg* cfg, int pair_index,
   if (cfg->ransac_iters > 0) { /* tracking_main.c:199-218 */
     float E[3][3];
     int ninl = 0;
-    orc_ransac_identity(nm, pts0, pts1, cfg->ransac_iters, cfg->ransac_thr, M, E, inl, &ninl);
+    /* the reference's inlier array holds MAX_NUM_INLIERS = 1000 entries (pnp_solver.c:107,:146) */
+    orc_ransac_identity(nm, pts0, pts1, cfg->ransac_iters, cfg->ransac_thr, M < 1000 ? M : 1000, E, inl, &ninl);
     out->ransac_inliers = ninl;
   }
 

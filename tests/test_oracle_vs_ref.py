@@ -179,6 +179,28 @@ def test_ransac_and_error_vs_reference(oracle, reference):
         assert a == b
 
 
+@pytest.mark.parametrize("n,frac_inl", [(1, 1.0), (7, 0.5), (150, 0.0), (999, 1.0), (1000, 1.0), (1001, 1.0),
+                                        (1500, 0.8), (4096, 0.3), (4096, 1.0)])
+def test_ransac_cap_and_empty_cases_vs_reference(oracle, reference, n, frac_inl):
+    """pnp_solver.c:110-165 beyond tracking_main's 150 points: the 1000-entry inlier array (:146 stops
+    counting there, :152 replaces the best on every iteration that reaches it), fewer points than the 8
+    draws, and no inlier at all (the reference writes nothing: *num_inliers keeps the caller's value; the
+    restatement reports wrote = 0 and the library's defined result is E = I, 0 inliers)."""
+    rng = np.random.default_rng(n)
+    p1 = (rng.random((n, 2)) * np.array([1241, 376])).astype(np.float32)
+    off = np.where(rng.random((n, 1)) < frac_inl, rng.random((n, 2)) * 1.4 - 0.7, 3.0 + rng.random((n, 2)))
+    p2 = (p1 + off.astype(np.float32)).astype(np.float32)
+    K = np.array([[718.856, 0, 607.1928], [0, 718.856, 185.2157], [0, 0, 1]], np.float32)
+    for iters, thr in ((10, 1.1), (1, 0.25), (3, 1e9)):
+        E1, inl1, n1 = reference.ransac(p1, p2, K, iters, thr)
+        E2, inl2, n2, wrote = oracle.ransac_identity(p1, p2, iters, thr)
+        if n1 < 0:                      # the reference never wrote its outputs
+            assert wrote == 0 and n2 == 0
+            continue
+        assert wrote == 1 and n1 == n2 and (inl1 == inl2).all() and (E1 == E2).all()
+        assert n1 <= 1000 and (thr < 1e8 or n1 == min(n, 1000))
+
+
 def test_svd3_vs_reference_random(oracle, reference):
     rng = np.random.default_rng(11)
     for i in range(50):
