@@ -89,6 +89,25 @@ def test_softmax_batch_unaligned_and_counts(tracker, oracle, synth):
         assert int(nv[f]) == n2 and (idx[f].cpu().numpy() == i2).all() and (bits(prob[f].cpu().numpy()) == bits(p2)).all()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_detector_on_adversarial_logits(tk, oracle, seed):
+    """tests/adversarial.py:adversarial_logits (ties inside cells, 127 under large scales, dustbin-only
+    and all-negative cells, probability ties at the top-N cut) through compute_softmax_ex /
+    compute_top_N_ex against T2, which test_t2_equals_t1_on_adversarial_logits pins to T1
+    (top_N.c:22-49 first-wins argmax, :77 threshold, :108-133 first N in patch order)."""
+    from adversarial import adversarial_logits
+    semi = adversarial_logits(seed)
+    for scale in (0.01, 0.35622698, 1.0, 3.0):
+        i1, p1, n1 = tk.compute_softmax(scale, semi)
+        i2, p2, n2 = oracle.softmax(scale, semi)
+        assert n1 == n2 and (i1 == i2).all() and (bits(p1) == bits(p2)).all()
+        for N in (100, 37, 1):
+            a = tk.compute_top_N(scale, semi, N, max_valid=1000)
+            b = oracle.top_n(scale, semi, N, max_valid=1000)
+            assert len(a[0]) == len(b[0])
+            assert (a[0] == b[0]).all() and (a[1] == b[1]).all() and (bits(a[2]) == bits(b[2])).all()
+
+
 # ------------------------------------------------------------------ matcher
 def _oracle_pair(oracle, rows, cols, s0, d0, s1, d1, N, M, radius=4, shift=(4, 4), scale=None, max_valid=None):
     scale = float(scale)
@@ -218,6 +237,31 @@ def test_ransac_batch_device_pose(tracker, oracle, kat):
         assert (bits(got[:9]) == bits(kat["pose_R1"].reshape(-1))).all() and (bits(got[9:]) == bits(kat["pose_t"])).all()
 
 
+def test_ransac_batch_inlier_cap(tracker, oracle):
+    """pnp_solver.c:107,:146,:152: the inlier array holds 1000 entries.  Pairs of 1024 points with 0, 7,
+    999, 1000, 1001 and 1024 inliers: counts and the ordered inlier lists against T2 with cap = 1000
+    (T2 == T1 on these shapes: test_ransac_cap_and_empty_cases_vs_reference)."""
+    import torch
+    rng = np.random.default_rng(9)
+    wants = [0, 7, 999, 1000, 1001, 1024]
+    P, M = len(wants), 1024
+    pts = np.zeros((P, M, 4), np.float32)
+    for p, k in enumerate(wants):
+        a = (rng.random((M, 2)) * np.array([1241, 376])).astype(np.float32)
+        inl = np.zeros(M, bool)
+        inl[rng.permutation(M)[:k]] = True
+        off = np.where(inl[:, None], rng.random((M, 2)) * 1.2 - 0.6, 4.0 + rng.random((M, 2)))
+        pts[p, :, :2] = a
+        pts[p, :, 2:] = a + off.astype(np.float32)
+    cnt = np.full(P, M, np.int32)
+    ninl, inl, _ = tracker.ransac_identity(torch.from_numpy(pts).to(tracker.device),
+                                           torch.from_numpy(cnt).to(tracker.device))
+    for p, k in enumerate(wants):
+        E, ref_inl, n, _ = oracle.ransac_identity(pts[p, :, :2], pts[p, :, 2:], cap=1000)
+        assert n == min(k, 1000) == int(ninl[p])
+        assert (inl[p, :n].cpu().numpy() == ref_inl).all()
+
+
 def test_matmul_shim(tk, kat):
     A, B = kat["mm_A"].copy(), kat["mm_B"].copy()
     C1 = kat["mm_C0"].copy()
@@ -263,18 +307,23 @@ def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, sample_size, n, str
     cfg = orc.pnp_cfg(hypotheses=H, seed=4, lanes=lanes, sample_size=sample_size)
     for p in range(P):
         rp, rs, rh = oracle.pnp_gn(cfg, corr[p], n, pair_index=p, want_hyp=True)
-        # per hypothesis: same inlier count, pose within tolerance
-        assert (hyp[p, :, 7] == rh[:, 7]).mean() > 0.97
-        # hypotheses that found a consensus (the others are chaotic by nature and may be inf)
-        good = (rh[:, 7] >= 0.3 * n) & (hyp[p, :, 7] == rh[:, 7])
+        # Every hypothesis, bit for bit: the kernel follows the oracle operation for operation (explicit RN
+        # ops, -fmad=false), so pose and inlier count of all H hypotheses are identical -- including the
+        # chaotic ones that never found a consensus.  A hypothesis that diverged to NaN is NaN in both
+        # (payload and sign of a NaN are not part of the contract).
+        g, r = hyp[p], rh
+        same = (g.view(np.int32) == r.view(np.int32)) | (np.isnan(g) & np.isnan(r))
+        bad = np.nonzero(~same.all(axis=1))[0]
+        assert bad.size == 0, (lanes, n, "hypotheses that differ:", bad[:8].tolist(),
+                               g[bad[:3]].tolist(), r[bad[:3]].tolist())
+        # the 1e-5 rad / 1e-5 relative tolerance of BASELINE.json is therefore met with zero error;
+        # kept as a statement of the contract on the hypotheses that found a consensus
+        good = rh[:, 7] >= 0.3 * n
         assert good.sum() >= 1
         ang = np.array([rot_angle(hyp[p, h, :4], rh[h, :4]) for h in np.nonzero(good)[0]])
         dt = (np.linalg.norm(hyp[p, good, 4:7] - rh[good, 4:7], axis=1)
               / np.maximum(1.0, np.linalg.norm(rh[good, 4:7], axis=1)))
         assert (ang < 1e-5).all() and (dt < 1e-5).all()
-        # in practice the kernel follows the oracle operation for operation
-        bit_equal = (hyp[p].view(np.int32) == rh.view(np.int32)).all(axis=1).mean()
-        assert bit_equal > 0.9, bit_equal
         # selected pose: tolerance stated in BASELINE.json north_star
         assert stats[p, 0] == rs[0] and stats[p, 3] == rs[3]
         assert rot_angle(pose[p, :4], rp[:4]) < 1e-5
@@ -324,6 +373,66 @@ def test_track_sequence_vs_oracle(tracker, tk, oracle, synth, rows, cols, N, M, 
         assert got["pnp_inliers"] == ref.pnp_inliers
         assert rot_angle(got["q"], np.array(list(ref.q))) < 1e-5
         assert np.linalg.norm(got["t"] - np.array(list(ref.t))) <= 1e-5 * max(1.0, np.linalg.norm(list(ref.t)))
+
+
+def test_gpu_pose_agrees_with_cv2_on_bench_pairs(tracker, tk, synth):
+    """An independent solver on the GPU's own output at the bench shape (the Gauss-Newton PnP is parity-unpinned
+    by the reference, so this is the outside check of what the B200 returns, not only of the oracle): 128
+    pairs of the bench sequence (47x155 cells, top-1000 queries, 1024 hypotheses).  For every pair
+    cv2.solvePnP(ITERATIVE), started from nothing, on the consensus set of the GPU pose must land on the
+    same pose to 3e-3 rad / 0.05 (the data's noise level: 3-px gate, ~40 % inliers, poses of ~0.05 rad /
+    ~0.15; the GPU pose is 10 gated Gauss-Newton steps, cv2 the minimum on the final set) and the GPU pose's
+    reprojection RMS on that set is within 25 % of cv2's optimum (measured on
+    these 128 pairs with the bit-identical CPU oracle: worst 2.3e-3 rad, 0.025, 1.17x).  The records of mv_track_sequence carry
+    the same pose bytes."""
+    cv2 = pytest.importorskip("cv2")
+    import torch
+    rows, cols, n_frames = 47, 155, 129
+    off = synth.default_offsets(n_frames, 0)
+    semi, desc, depth = tracker.synth_frames(0, rows, cols, 0, off)
+    scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+    p = tk.kitti_track_params(top_n=1000, max_valid=8192, max_matches=1024, hypotheses=1024)
+    res = tk.results_to_numpy(tracker.track_sequence(p, semi, scale, desc, depth))
+    idx, prob, _ = tracker.softmax(semi, scale)
+    qp, qi, _, qc, _ = tracker.top_n(idx, prob, 1000, 8192)
+    pts, cnt, cell0, _, _ = tracker.match(p.match, desc, idx, prob, qp, qi, qc)
+    cam = (p.pnp.fx, p.pnp.fy, p.pnp.cx, p.pnp.cy)
+    corr = tracker.build_corr(pts, cnt, cell0, depth, cam, rows)
+    pose, stats, _ = tracker.pnp_gn(p.pnp, corr, cnt)
+    pose, stats, corr, cnt = pose.cpu().numpy(), stats.cpu().numpy(), corr.cpu().numpy(), cnt.cpu().numpy()
+    K = np.array([[cam[0], 0, cam[2]], [0, cam[1], cam[3]], [0, 0, 1]], np.float64)
+
+    def q2R(q):
+        w, x, y, z = q
+        return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                         [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                         [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+
+    def project(R, t, X):
+        Xc = X @ R.T + t
+        return np.stack([cam[0] * Xc[:, 0] / Xc[:, 2] + cam[2], cam[1] * Xc[:, 1] / Xc[:, 2] + cam[3]], 1)
+
+    checked = 0
+    for i in range(n_frames - 1):
+        assert res[i]["num_matches"] == cnt[i]
+        assert np.array_equal(bits(res[i]["q"]), bits(pose[i, :4])) and np.array_equal(bits(res[i]["t"]), bits(pose[i, 4:]))
+        n = int(cnt[i])
+        if stats[i, 3] != 1 or stats[i, 0] < 30:
+            continue
+        X, z = corr[i, :3, :n].T.astype(np.float64), corr[i, 3:5, :n].T.astype(np.float64)
+        R, t = q2R(pose[i, :4].astype(np.float64)), pose[i, 4:].astype(np.float64)
+        cons = ((project(R, t, X) - z) ** 2).sum(1) < p.pnp.gate_sq
+        assert abs(int(cons.sum()) - int(stats[i, 0])) <= 2      # float64 re-evaluation of the fp32 gate
+        ok, rvec, tvec = cv2.solvePnP(X[cons], z[cons], K, None, flags=cv2.SOLVEPNP_ITERATIVE)
+        assert ok
+        Rcv, _ = cv2.Rodrigues(rvec)
+        ang = np.arccos(np.clip((np.trace(Rcv @ R.T) - 1) / 2, -1, 1))
+        assert ang < 3e-3 and np.linalg.norm(tvec.ravel() - t) < 0.05, (i, ang, tvec.ravel(), t)
+        rms_gpu = np.sqrt(((project(R, t, X[cons]) - z[cons]) ** 2).sum(1).mean())
+        rms_cv = np.sqrt(((project(Rcv, tvec.ravel(), X[cons]) - z[cons]) ** 2).sum(1).mean())
+        assert rms_gpu <= 1.25 * rms_cv + 1e-6, (i, rms_gpu, rms_cv)
+        checked += 1
+    assert checked >= 100, checked
 
 
 def test_track_sequence_tensor_core_matcher_same_bytes(tracker, tk, synth):
