@@ -14,6 +14,19 @@
  *       semi [cells][65], desc [cells][256], cell = col*rows + row (column-major,
  *       tracking_main.c:59-66); a batch is n_frames of them back to back
  *   - caller owns all buffers; the context owns only its scratch
+ *
+ * Device and thread contract
+ *   - a context belongs to the GPU given to mv_ctx_create.  Every entry point that takes a
+ *     context makes that GPU current for the duration of the call and restores the calling
+ *     thread's current device before it returns (mv_ctx_create included), so contexts of
+ *     different GPUs can be used from one thread and a context can be used from any thread
+ *   - a context is not internally locked: one call at a time per context (one context per
+ *     host thread or per GPU is the intended use); different contexts are independent.  The
+ *     legacy void symbols share one process-global context on device 0 behind a mutex
+ *   - batched calls take at most 65535 pairs / frames (MV_ERR_BAD_ARG beyond that; the
+ *     host-buffer sequence call chunks internally and has no such limit)
+ *   - on any error return of mv_track_sequence_host the library has drained its streams:
+ *     the caller's host buffers are no longer read when the call returns
  */
 #ifndef MAVERIC_B200_H
 #define MAVERIC_B200_H

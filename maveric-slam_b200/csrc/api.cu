@@ -45,7 +45,9 @@ extern "C" mv_status mv_ctx_create(int device, mv_ctx** out) {
     cudaGetLastError();
     return MV_ERR_NO_DEVICE;  // kernels are sm_100a only
   }
-  if (cudaSetDevice(device) != cudaSuccess) return MV_ERR_NO_DEVICE;
+  mv_device_guard guard(device);   // the caller's current device is restored on return
+  int cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != device) { cudaGetLastError(); return MV_ERR_NO_DEVICE; }
   mv_ctx* c = new mv_ctx();
   c->device = device;
   c->sm_count = prop.multiProcessorCount;
@@ -56,6 +58,10 @@ extern "C" mv_status mv_ctx_create(int device, mv_ctx** out) {
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaStreamCreateWithPriority(&c->copy_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaStreamCreateWithPriority(&c->gather_stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) {
+    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->gather_stream) cudaStreamDestroy(c->gather_stream);
+    cudaGetLastError();
     delete c;
     return MV_ERR_CUDA;
   }
@@ -65,13 +71,14 @@ extern "C" mv_status mv_ctx_create(int device, mv_ctx** out) {
 
 extern "C" void mv_ctx_destroy(mv_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  mv_device_guard guard(c->device);
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->gather_stream);
   for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
   for (auto& kv : c->scratch) cudaFree(kv.second.first);
   if (c->pinned) cudaFreeHost(c->pinned);
+  if (c->abort_host) cudaFreeHost(c->abort_host);
   if (c->own_stream) cudaStreamDestroy(c->stream);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->gather_stream);
@@ -79,7 +86,7 @@ extern "C" void mv_ctx_destroy(mv_ctx* c) {
 }
 
 extern "C" mv_status mv_ctx_set_stream(mv_ctx* c, void* s) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
   c->stream = (cudaStream_t)s;
   c->own_stream = false;
@@ -87,7 +94,7 @@ extern "C" mv_status mv_ctx_set_stream(mv_ctx* c, void* s) {
 }
 
 extern "C" mv_status mv_ctx_sync(mv_ctx* c) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   MV_CUDA(c, cudaStreamSynchronize(c->stream));
   return MV_OK;
 }
@@ -96,7 +103,7 @@ extern "C" const char* mv_last_error(mv_ctx* c) { return c ? c->err : "null cont
 extern "C" unsigned long long mv_ctx_launch_count(mv_ctx* c) { return c ? c->launches : 0; }
 
 extern "C" mv_status mv_ctx_profile(mv_ctx* c, int enable) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   c->profile = enable != 0;
   for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
   c->pending.clear();
@@ -105,7 +112,8 @@ extern "C" mv_status mv_ctx_profile(mv_ctx* c, int enable) {
 }
 
 extern "C" mv_status mv_ctx_profile_read(mv_ctx* c, const char* tag, double* avg_ms, int* launches) {
-  if (!c || !tag) return MV_ERR_BAD_ARG;
+  if (!tag) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   MV_CUDA(c, cudaStreamSynchronize(c->stream));
   for (auto& ev : c->pending) {
     float ms = 0.f;
@@ -137,6 +145,15 @@ mv_status mv_scratch(mv_ctx* c, const char* name, size_t bytes, void** out) {
     slot.second = want;
   }
   *out = slot.first;
+  return MV_OK;
+}
+
+mv_status mv_abort_flag(mv_ctx* c, int** out) {
+  if (!c->abort_host) {
+    MV_CUDA(c, cudaHostAlloc((void**)&c->abort_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    *c->abort_host = 0;
+  }
+  *out = c->abort_host;   // unified addressing: the same pointer is valid on the device
   return MV_OK;
 }
 
@@ -198,7 +215,7 @@ static mv_status detect_one(mv_ctx* c, float scale, const int8_t* h_semi, int ce
 
 extern "C" mv_status compute_softmax_ex(mv_ctx* c, float scale, const int8_t* h_semi, int cells,
                                         int* num_valid, int* max_indices, float* probs) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (!h_semi || cells <= 0 || !max_indices || !probs) MV_BAD_ARG(c, "compute_softmax_ex");
   int32_t *di, *dn; float* dp;
   mv_status st = detect_one(c, scale, h_semi, cells, &di, &dp, &dn);
@@ -215,7 +232,7 @@ extern "C" mv_status compute_softmax_ex(mv_ctx* c, float scale, const int8_t* h_
 extern "C" mv_status compute_top_N_ex(mv_ctx* c, float scale, const int8_t* h_semi, int cells, int N,
                                       int max_valid, int* num_selected, int* N_patches, int* N_indices,
                                       float* N_probs) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (!h_semi || cells <= 0 || N <= 0 || max_valid <= 0 || !num_selected || !N_patches || !N_indices || !N_probs)
     MV_BAD_ARG(c, "compute_top_N_ex");
   int32_t *di, *dn; float* dp;
@@ -275,7 +292,7 @@ extern "C" mv_status mv_match_pair_host(mv_ctx* c, const mv_match_params* p, con
                                         int num_queries, const int* patches1, const int* indices1,
                                         float* points1, float* points2, int* num_matches, int* cell0,
                                         float* score) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (!p || !h_desc0 || !h_desc1 || !max_indices0 || !probs0 || num_queries < 0 || !points1 || !points2 ||
       !num_matches)
     MV_BAD_ARG(c, "mv_match_pair_host");
@@ -362,6 +379,7 @@ extern "C" void ransac_essential_matrix(const int num_points, const float points
   (void)K;
   std::lock_guard<std::mutex> lk(g_mu);
   mv_ctx* c = legacy_ctx();
+  mv_device_guard guard(c->device);
   // Defined result where the reference has none (no match / no inlier).
   for (int i = 0; i < 3; i++)
     for (int j = 0; j < 3; j++) best_E[i][j] = i == j ? 1.0f : 0.0f;
@@ -475,6 +493,7 @@ static mv_status matmul_host(mv_ctx* c, size_t I, size_t J, size_t K, const floa
                              const float* D, float* C, size_t sA, size_t sB, size_t sD, size_t sC, float as,
                              float bs, float ds, bool tA, bool tB) {
   if (I == 0 || J == 0) return MV_OK;
+  mv_device_guard guard(c->device);
   const size_t nA = K == 0 ? 0 : (tA ? (K - 1) * sA + I : (I - 1) * sA + K);
   const size_t nB = K == 0 ? 0 : (tB ? (J - 1) * sB + K : (K - 1) * sB + J);
   const size_t nC = (I - 1) * sC + J;
@@ -649,10 +668,12 @@ static mv_status seq_match_pose(mv_ctx* c, const mv_track_params* p, int n_frame
 extern "C" mv_status mv_track_sequence(mv_ctx* c, const mv_track_params* p, int n_frames, const int8_t* d_semi,
                                        const float* d_semi_scale, const int8_t* d_desc, const float* d_depth,
                                        mv_pair_result* d_results) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (!p || n_frames < 2 || !d_semi || !d_semi_scale || !d_desc || !d_depth || !d_results)
     MV_BAD_ARG(c, "mv_track_sequence");
   if (!seq_params_ok(p)) MV_BAD_ARG(c, "mv_track_sequence: rows, cols, top_n, max_valid and max_matches must be positive");
+  if (n_frames > 65535)
+    MV_BAD_ARG(c, "mv_track_sequence: at most 65535 frames per call (grid y dimension); mv_track_sequence_host chunks longer sequences");
   SeqScratch w;
   mv_status st;
   if ((st = seq_scratch(c, p, n_frames, "seq", &w))) return st;
@@ -695,7 +716,7 @@ __global__ void mark_query_rows_kernel(int cells, int top_n, const int32_t* __re
 constexpr int kGatherStages = 2;
 __global__ void __launch_bounds__(32)
 gather_rows_kernel(long long total_cells, const uint8_t* __restrict__ flags, const int8_t* __restrict__ h_desc,
-                   int8_t* __restrict__ d_desc, unsigned long long* __restrict__ rows_moved) {
+                   int8_t* __restrict__ d_desc, unsigned long long* __restrict__ rows_moved, int* abort_flag) {
   __shared__ __align__(128) uint8_t slots[kGatherStages][32][256];
   __shared__ uint64_t bar[kGatherStages];
   __shared__ long long queue[64];
@@ -715,7 +736,7 @@ gather_rows_kernel(long long total_cells, const uint8_t* __restrict__ flags, con
 
   auto flush_pending = [&]() {       // wait for the in-flight stage, then store its rows
     if (pend_stage < 0) return;
-    sm100::mbar_wait(sm100::smem_u32(&bar[pend_stage]), (used[pend_stage] - 1) & 1, nullptr, 9);
+    sm100::mbar_wait(sm100::smem_u32(&bar[pend_stage]), (used[pend_stage] - 1) & 1, abort_flag, 9);
     if (pend_cell >= 0)
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], 256;"
                    ::"l"(reinterpret_cast<uint64_t>(d_desc + pend_cell * 256)),
@@ -793,7 +814,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
                                             const int8_t* h_desc, const float* h_depth,
                                             mv_pair_result* h_results, unsigned long long* h2d_bytes,
                                             unsigned long long* d2h_bytes) {
-  if (!c) return MV_ERR_BAD_ARG;
+  MV_ENTER(c);
   if (!p || n_frames < 2 || !h_semi || !h_semi_scale || !h_desc || !h_depth || !h_results)
     MV_BAD_ARG(c, "mv_track_sequence_host");
   if (!seq_params_ok(p))
@@ -850,11 +871,24 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
   }
   if ((st = mv_scratch(c, "host.results", sizeof(mv_pair_result) * (size_t)n_pairs, &dres))) return st;
   if ((st = mv_scratch(c, "host.moved", 16, &dmoved))) return st;
+  int* abort_flag = nullptr;
+  if ((st = mv_abort_flag(c, &abort_flag))) return st;
   // every event of this call lives in `events` and is destroyed on any return path
   struct EventBag {
     std::vector<cudaEvent_t> v;
     ~EventBag() { for (cudaEvent_t e : v) cudaEventDestroy(e); }
   } events;
+  // On every return path -- errors included -- the three streams are drained before the events die and
+  // before the caller gets its buffers back: the DMA engine and the row-gather kernel read the caller's
+  // pinned h_semi / h_desc / h_depth asynchronously.
+  struct Drain {
+    mv_ctx* c;
+    ~Drain() {
+      cudaStreamSynchronize(c->stream);
+      cudaStreamSynchronize(c->copy_stream);
+      cudaStreamSynchronize(c->gather_stream);
+    }
+  } drain{c};
   auto new_event = [&](cudaEvent_t* e) -> mv_status {
     MV_CUDA(c, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     events.v.push_back(*e);
@@ -948,7 +982,7 @@ extern "C" mv_status mv_track_sequence_host(mv_ctx* c, const mv_track_params* p,
     }
     gather_rows_kernel<<<c->sm_count, 32, 0, gs>>>((long long)nf * cells, w[b].flags,
                                                    hd_desc + (size_t)p0 * cells * 256, (int8_t*)bd[b],
-                                                   (unsigned long long*)dmoved);
+                                                   (unsigned long long*)dmoved, abort_flag);
     MV_CHECK_LAUNCH(c);
     MV_CUDA(c, cudaEventRecord(ready[b], gs));
     mark("gat_end", k, gs);

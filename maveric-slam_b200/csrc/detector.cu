@@ -250,7 +250,7 @@ top_n_kernel(const int32_t* __restrict__ max_idx, const float* __restrict__ prob
 extern "C" mv_status mv_softmax_batch(mv_ctx* ctx, int n_frames, int cells, const int8_t* d_semi,
                                       const float* d_semi_scale, int32_t* d_max_idx, float* d_prob,
                                       int32_t* d_num_valid) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_frames <= 0 || cells <= 0 || !d_semi || !d_semi_scale || !d_max_idx || !d_prob)
     MV_BAD_ARG(ctx, "mv_softmax_batch");
   const long long total = (long long)n_frames * cells;
@@ -267,7 +267,7 @@ extern "C" mv_status mv_top_n_batch(mv_ctx* ctx, int n_frames, int cells, int to
                                     const int32_t* d_max_idx, const float* d_prob, int32_t* d_q_patch,
                                     int32_t* d_q_idx, float* d_q_prob, int32_t* d_q_count,
                                     int32_t* d_overflow) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_frames <= 0 || cells <= 0 || top_n <= 0 || max_valid <= 0 || !d_max_idx || !d_prob ||
       !d_q_patch || !d_q_idx || !d_q_prob || !d_q_count)
     MV_BAD_ARG(ctx, "mv_top_n_batch");

@@ -465,7 +465,7 @@ lba_solve_kernel(int n_windows, int n_poses, float damping, const float* __restr
 
 extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks, int n_poses, int chunk,
                                         const float* d_J, float* d_C) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_windows <= 0 || n_ldmks <= 0 || n_poses <= 0 || chunk <= 0 || !d_J || !d_C)
     MV_BAD_ARG(ctx, "mv_lba_schur_batch");
   if (n_ldmks % chunk != 0 || n_poses > 16 || chunk > 16)
@@ -487,7 +487,7 @@ extern "C" mv_status mv_lba_schur_batch(mv_ctx* ctx, int n_windows, int n_ldmks,
 
 extern "C" mv_status mv_lba_solve_batch(mv_ctx* ctx, int n_windows, int n_poses, float damping,
                                         const float* d_C, float* d_delta, int32_t* d_ok) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_windows <= 0 || n_poses <= 0 || !d_C || !d_delta || !d_ok) MV_BAD_ARG(ctx, "mv_lba_solve_batch");
   if (n_poses > 16) MV_BAD_ARG(ctx, "mv_lba_solve_batch: n_poses <= 16");
   const int n = 6 * n_poses;

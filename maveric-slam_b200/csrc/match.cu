@@ -253,13 +253,15 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
                                     const int32_t* d_q_patch, const int32_t* d_q_idx,
                                     const int32_t* d_q_count, float* d_match_pts, int32_t* d_match_count,
                                     int32_t* d_match_cell0, int32_t* d_match_query, float* d_match_score) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (!p || n_pairs <= 0 || top_n <= 0 || !d_desc || !d_max_idx || !d_prob || !d_q_patch || !d_q_idx ||
       !d_q_count || !d_match_pts || !d_match_count || p->rows <= 0 || p->cols <= 0 || p->radius < 0 ||
       p->max_matches <= 0)
     MV_BAD_ARG(ctx, "mv_match_batch");
   if ((reinterpret_cast<uintptr_t>(d_desc) & 15) || (reinterpret_cast<uintptr_t>(d_match_pts) & 15))
     MV_BAD_ARG(ctx, "mv_match_batch: d_desc and d_match_pts must be 16-byte aligned");
+  if (n_pairs > 65535 || n_frames > 65535)
+    MV_BAD_ARG(ctx, "mv_match_batch: at most 65535 pairs / frames per call (grid y dimension); split the batch");
   const int cells = p->rows * p->cols;
   int use_tc = p->use_tensor_cores;
   if (use_tc == 2) use_tc = (p->rows <= 256 && n_frames > 0 && p->match_threshold * p->match_threshold >= 0.0) ? 1 : 0;

@@ -604,10 +604,10 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   g.accept_gt = mv_round_down(thr2);
   g.prob_lt = mv_round_up(p->min_prob0);
 
-  void* vb = nullptr; void* flag = nullptr;
+  void* vb = nullptr; int* flag = nullptr;
   mv_status st = mv_scratch(ctx, "match.vbits", sizeof(uint32_t) * (size_t)n_frames * g.vwords, &vb);
   if (st) return st;
-  st = mv_scratch(ctx, "match.tc_abort", 256, &flag);
+  st = mv_abort_flag(ctx, &flag);
   if (st) return st;
   void* spans = nullptr;
   st = mv_scratch(ctx, "match.tc_spans", sizeof(int4) * (size_t)g.n_items, &spans);
@@ -628,7 +628,6 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
 
   mv_prof_scope ps(ctx, "match");
   MV_CUDA(ctx, cudaMemsetAsync(vb, 0, sizeof(uint32_t) * (size_t)n_frames * g.vwords, ctx->stream));
-  MV_CUDA(ctx, cudaMemsetAsync(flag, 0, 4, ctx->stream));
   {
     dim3 grid((g.cells + 255) / 256, n_frames);
     valid_bits_kernel<<<grid, 256, 0, ctx->stream>>>(g.cells, g.vwords, g.prob_lt, d_max_idx, d_prob, (uint32_t*)vb);
@@ -643,7 +642,7 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   MV_CUDA(ctx, cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = g.n_items < ctx->sm_count ? g.n_items : ctx->sm_count;
   match_tc_kernel<<<grid, kThreads, smem, ctx->stream>>>(tmap, g, d_f0, d_f1, d_desc, (const uint32_t*)vb, d_q_patch,
-                                                        d_q_count, (const int4*)spans, d_best_cell, d_best_score, (size_t)n_pairs * (size_t)top_n, (int*)flag);
+                                                        d_q_count, (const int4*)spans, d_best_cell, d_best_score, (size_t)n_pairs * (size_t)top_n, flag);
   MV_CHECK_LAUNCH(ctx);
   return MV_OK;
 }

@@ -40,6 +40,10 @@ struct mv_ctx {
 
   // scratch arena, grown on demand, never shrunk; owned by the context
   std::map<std::string, std::pair<void*, size_t>> scratch;
+  // Wait-site diagnostic of the mbarrier pipelines (tcgen05 matcher, TMA row gather): one int in mapped
+  // pinned host memory, written by a kernel just before it traps on a barrier that never completed.  Host
+  // memory survives the sticky error a trap leaves behind, so MV_CUDA can still name the wait site.
+  int* abort_host = nullptr;
   // pinned host mirror for small synchronous host-pointer calls
   void* pinned = nullptr;
   size_t pinned_bytes = 0;
@@ -49,11 +53,16 @@ struct mv_ctx {
   do {                                                                              \
     cudaError_t e__ = (call);                                                       \
     if (e__ != cudaSuccess) {                                                       \
-      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s", __FILE__, __LINE__, \
-               #call, cudaGetErrorString(e__));                                     \
+      const int site__ = (ctx)->abort_host ? *(volatile int*)(ctx)->abort_host : 0; \
+      snprintf((ctx)->err, sizeof((ctx)->err), "%s:%d %s -> %s%s%.0d", __FILE__, __LINE__, \
+               #call, cudaGetErrorString(e__),                                      \
+               site__ ? " (an mbarrier wait timed out in a pipeline kernel, wait site " : "", \
+               site__ ? site__ - 0x1000 : 0);                                       \
       return MV_ERR_CUDA;                                                           \
     }                                                                               \
   } while (0)
+
+mv_status mv_abort_flag(mv_ctx* ctx, int** out);
 
 #define MV_CHECK_LAUNCH(ctx)                                                        \
   do {                                                                              \
@@ -91,6 +100,25 @@ struct mv_prof_scope {
     ctx->pending.push_back(ev);
   }
 };
+
+
+// Device contract (include/maveric_b200.h): a context belongs to one GPU; every entry point that takes
+// a context makes that GPU current for the duration of the call and restores the caller's device on
+// return, so contexts of different GPUs may be used from one thread and a context from any thread.
+struct mv_device_guard {
+  int prev = -1;
+  bool switched = false;
+  explicit mv_device_guard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; }
+    if (prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~mv_device_guard() {
+    if (switched && prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define MV_ENTER(ctx)                       \
+  if (!(ctx)) return MV_ERR_BAD_ARG;        \
+  mv_device_guard mv_guard__((ctx)->device)
 
 mv_status mv_scratch(mv_ctx* ctx, const char* name, size_t bytes, void** out);
 mv_status mv_pinned(mv_ctx* ctx, size_t bytes, void** out);

@@ -85,7 +85,7 @@ nms_wavefront_kernel(int n_frames, int rows, int cols, int32_t* __restrict__ max
 }  // namespace
 
 extern "C" mv_status mv_nms_batch(mv_ctx* ctx, int n_frames, int rows, int cols, int32_t* d_max_idx, float* d_prob) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_frames <= 0 || rows <= 0 || cols <= 0 || !d_max_idx || !d_prob) MV_BAD_ARG(ctx, "mv_nms_batch");
   mv_prof_scope ps(ctx, "nms");
   nms_wavefront_kernel<<<(n_frames + kNmsWarpsPerCta - 1) / kNmsWarpsPerCta, kNmsWarpsPerCta * 32, 0, ctx->stream>>>(
@@ -95,7 +95,7 @@ extern "C" mv_status mv_nms_batch(mv_ctx* ctx, int n_frames, int rows, int cols,
 }
 
 extern "C" mv_status run_nms_ex(mv_ctx* ctx, int rows, int cols, int* max_indices, float* probs) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (rows <= 0 || cols <= 0 || !max_indices || !probs) MV_BAD_ARG(ctx, "run_nms_ex");
   const size_t cells = (size_t)rows * cols;
   void *di, *dp;

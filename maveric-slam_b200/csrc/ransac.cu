@@ -58,7 +58,7 @@ extern "C" mv_status mv_ransac_identity_batch(mv_ctx* ctx, int n_pairs, int stri
                                               const int32_t* d_count, int num_iterations,
                                               float inlier_threshold, int32_t* d_num_inliers,
                                               int32_t* d_inliers, float* d_pose) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n_pairs <= 0 || stride_pts <= 0 || !d_pts || !d_count || !d_num_inliers)
     MV_BAD_ARG(ctx, "mv_ransac_identity_batch");
   mv_prof_scope ps(ctx, "ransac");

@@ -2,8 +2,10 @@
 // mbarrier, TMA (cp.async.bulk.tensor), tcgen05 (alloc / mma / commit / ld) and the shared-memory
 // and instruction descriptors of the UMMA unit.  Inline PTX only; no library templates.
 //
-// Every wait is bounded: a barrier that does not complete within ~2 s of polling sets
-// *mv_tc_abort and traps, so a protocol bug surfaces as a launch failure, never as a hung GPU.
+// Every wait is bounded: a barrier that does not complete within MV_MBAR_TIMEOUT_NS (10 s by default;
+// compile with -DMV_MBAR_TIMEOUT_NS=0 for unbounded waits under a debugger or sanitizer) writes its wait
+// site into a flag in mapped host memory and traps, so a protocol bug surfaces as a launch failure that
+// names the site (mv_last_error), never as a hung GPU.
 #pragma once
 
 #include <cuda.h>
@@ -40,7 +42,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: polls, and every 256 probes checks the global nanosecond timer; a barrier
-// that has not completed after 2 s flags *abort_flag and traps.
+// that has not completed after MV_MBAR_TIMEOUT_NS flags *abort_flag (mapped host memory) and traps.
+#ifndef MV_MBAR_TIMEOUT_NS
+#define MV_MBAR_TIMEOUT_NS 10000000000ull
+#endif
 __device__ __forceinline__ uint64_t globaltimer_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -64,13 +69,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* ab
   for (uint32_t i = 1;; i++) {
     if (mbar_try_wait(bar, parity)) { MV_TC_TRACE_ADD(who, c0); return; }
     if (backoff_ns) __nanosleep(backoff_ns);
-    if ((i & 255u) == 0) {
+    if (MV_MBAR_TIMEOUT_NS != 0 && (i & 255u) == 0) {
       const uint64_t t = globaltimer_ns();
       if (t0 == 0) t0 = t;
-      else if (t - t0 > 2000000000ull) break;
+      else if (t - t0 > MV_MBAR_TIMEOUT_NS) break;
     }
   }
-  if (abort_flag) atomicExch(abort_flag, 0x1000 + who);
+  if (abort_flag) {
+    *reinterpret_cast<volatile int*>(abort_flag) = 0x1000 + who;
+    __threadfence_system();
+  }
   __trap();
 }
 

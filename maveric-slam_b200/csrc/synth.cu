@@ -75,7 +75,7 @@ __global__ void synth_frames_kernel(unsigned long long ms, int rows, int cols, i
 
 extern "C" mv_status mv_synth_frames(mv_ctx* ctx, const mv_synth_params* p, int first_frame, int n_frames,
                                      const int32_t* d_off, int8_t* d_semi, int8_t* d_desc, float* d_depth) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (!p || n_frames <= 0 || !d_off || !d_semi || !d_desc || p->rows <= 0 || p->cols <= 0)
     MV_BAD_ARG(ctx, "mv_synth_frames");
   if (reinterpret_cast<uintptr_t>(d_desc) & 7) MV_BAD_ARG(ctx, "mv_synth_frames: d_desc must be 8-byte aligned");

@@ -128,7 +128,7 @@ __global__ void results_to_transforms_kernel(int n, const mv_pair_result* __rest
 }  // namespace
 
 extern "C" mv_status mv_chain_transforms(mv_ctx* ctx, int n, const double* d_transforms, double* d_traj) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n < 0 || !d_traj || (n > 0 && !d_transforms)) MV_BAD_ARG(ctx, "mv_chain_transforms");
   mv_prof_scope ps(ctx, "chain");
   chain_transforms_kernel<<<1, kScanThreads, 0, ctx->stream>>>(n, d_transforms, d_traj);
@@ -138,7 +138,7 @@ extern "C" mv_status mv_chain_transforms(mv_ctx* ctx, int n, const double* d_tra
 
 extern "C" mv_status mv_results_to_transforms(mv_ctx* ctx, int n, const mv_pair_result* d_results,
                                               double* d_transforms) {
-  if (!ctx) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
   if (n <= 0 || !d_results || !d_transforms) MV_BAD_ARG(ctx, "mv_results_to_transforms");
   results_to_transforms_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(n, d_results, d_transforms);
   MV_CHECK_LAUNCH(ctx);
