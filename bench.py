@@ -405,7 +405,7 @@ def main():
     else:
         match_entry = None
     rooflines = [
-        {"kernel": ("pnp_gn_sorted_kernel (K3)" if args.lanes == 1 else "pnp_gn_kernel<%d> (K3)" % args.lanes), "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
+        {"kernel": ("pnp_gn_twophase_kernel (K3)" if args.lanes == 1 else "pnp_gn_kernel<%d> (K3)" % args.lanes), "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
          "peak": fp32_nominal, "unit": "TFLOP/s",
          "frac": (pnp_flops / (pnp_ms * 1e-3) / 1e12) / fp32_nominal if pnp_ms else None,
          "ms_per_launch": pnp_ms, "algorithmic_flops": pnp_flops,

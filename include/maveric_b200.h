@@ -193,6 +193,10 @@ void mv_pnp_params_default(mv_pnp_params* p);
  *   d_pose      float [n_pairs][7]  best hypothesis
  *   d_stats     float [n_pairs][4]  {inliers, cost, best_h, valid}
  *   d_hyp_pose  float [n_pairs][H][8] every hypothesis {q,t,inliers} (nullable) */
+/* lanes_per_hypothesis: 1 = one thread per hypothesis (throughput form), 32 = one warp per hypothesis
+ * (latency form).  2, 4, 8, 16 are superseded A/B forms that exist only in a library built with
+ * -DMV_PNP_AB (mv_pnp_has_ab_forms() == 1); the product library answers MV_ERR_BAD_ARG for them. */
+int mv_pnp_has_ab_forms(void);
 mv_status mv_pnp_gn_batch(mv_ctx* ctx, const mv_pnp_params* p, int n_pairs, int stride,
                           const float* d_corr, const int32_t* d_count,
                           const float* d_init_pose,

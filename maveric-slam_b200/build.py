@@ -20,6 +20,8 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
           "-I", os.path.join(HERE, "..", "include")]
+if os.environ.get("MV_PNP_AB"):   # also compile the superseded K3 forms (A/B timing, tools/k3_ab.py)
+    COMMON.append("-DMV_PNP_AB")
 SOURCES = ["api.cu", "detector.cu", "match.cu", "match_tc.cu", "ransac.cu", "pnp_gn.cu", "traj.cu", "nms.cu", "lba.cu", "synth.cu", "pool.cpp"]
 
 

@@ -18,7 +18,7 @@ MV_OK, MV_ERR_NO_DEVICE, MV_ERR_CUDA, MV_ERR_BAD_ARG, MV_ERR_TOO_MANY_VALID = ra
 # Every symbol include/maveric_b200.h and include/maveric_slam_compat.h declare.
 NEW_SYMBOLS = [
     "mv_ctx_create", "mv_ctx_destroy", "mv_ctx_set_stream", "mv_ctx_sync", "mv_last_error", "mv_status_str",
-    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_ctx_pnp_work", "mv_softmax_batch", "mv_top_n_batch",
+    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_ctx_pnp_work", "mv_pnp_has_ab_forms", "mv_softmax_batch", "mv_top_n_batch",
     "compute_softmax_ex", "compute_top_N_ex", "mv_match_params_default", "mv_match_batch",
     "mv_match_pair_host", "mv_ransac_identity_batch", "mv_pnp_params_default", "mv_pnp_gn_batch",
     "mv_build_corr_batch", "mv_track_params_default", "mv_track_sequence", "mv_track_sequence_host",
@@ -103,6 +103,8 @@ def load() -> C.CDLL:
     L.mv_ctx_profile.argtypes = [vp, i32]
     L.mv_ctx_profile_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i32)]
     L.mv_ctx_pnp_work.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.mv_pnp_has_ab_forms.argtypes = []
+    L.mv_pnp_has_ab_forms.restype = i32
     L.mv_lba_schur_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp]
     L.mv_lba_solve_batch.argtypes = [vp, i32, i32, C.c_float, vp, vp, vp]
     L.mv_softmax_batch.argtypes = [vp, i32, i32, vp, vp, vp, vp, vp]

@@ -287,11 +287,15 @@ def _pnp_params(tk, H, lanes, seed=0, refine=10, sample_size=8):
     return p
 
 
-# lanes = 2 is the packed-FP32 (FFMA2) single-thread form; the others are LANES threads per hypothesis
-@pytest.mark.parametrize("lanes,sample_size", [(1, 8), (2, 8), (2, 7), (4, 8), (8, 8), (32, 8)])
-@pytest.mark.parametrize("n,stride", [(1000, 1024), (37, 64), (1500, 1536), (2049, 2304), (8, 8)])
+# lanes = 1: one thread per hypothesis (two-phase kernel for n <= 480, streaming kernel above); lanes = 32: one warp
+# per hypothesis.  lanes = 2 (packed-FP32 single thread), 4, 8 are A/B forms of a library built with -DMV_PNP_AB.
+@pytest.mark.parametrize("lanes,sample_size", [(1, 8), (1, 7), (2, 8), (2, 7), (4, 8), (8, 8), (32, 8)])
+@pytest.mark.parametrize("n,stride", [(1000, 1024), (37, 64), (330, 1024), (480, 512), (1500, 1536), (2049, 2304), (8, 8)])
 def test_pnp_gn_vs_oracle(tracker, tk, oracle, synth, lanes, sample_size, n, stride):
     import torch
+    from maveric_slam_b200 import lib
+    if lanes not in (1, 32) and not lib.load().mv_pnp_has_ab_forms():
+        pytest.skip("lanes 2..16 are A/B forms (build with MV_PNP_AB=1)")
     H, P = 96, 3
     corr = np.zeros((P, 5, stride), np.float32)
     truth = []

@@ -39,56 +39,54 @@ def _problems(synth, P, n, stride):
     return corr
 
 
-class _Form:
-    """MV_PNP_FORM for the duration of a block (the library reads it per call)."""
+class _Env:
+    """An environment variable for the duration of a block (the library reads its knobs per call)."""
 
-    def __init__(self, form):
-        self.form = form
+    def __init__(self, name, value):
+        self.name, self.value = name, value
 
     def __enter__(self):
-        self.old = os.environ.get("MV_PNP_FORM")
-        os.environ["MV_PNP_FORM"] = self.form
+        self.old = os.environ.get(self.name)
+        os.environ[self.name] = self.value
 
     def __exit__(self, *a):
         if self.old is None:
-            del os.environ["MV_PNP_FORM"]
+            del os.environ[self.name]
         else:
-            os.environ["MV_PNP_FORM"] = self.old
+            os.environ[self.name] = self.old
 
 
-@pytest.mark.parametrize("n,stride", [(1000, 1024), (330, 1024), (513, 640), (31, 32)])
+@pytest.mark.parametrize("n,stride", [(1000, 1024), (330, 1024), (480, 480), (481, 512), (513, 640), (31, 32), (3, 1024)])
 def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
-    """configs[2]: the sorted kernel (packed gate, per-lane mask walk, per-pass re-deal), the same
-    without the re-deal, the earlier mask kernel and the dense kernel: same bytes for every one of
-    1024 hypotheses and for the selected pose."""
+    """configs[2]: the product's two one-thread-per-hypothesis kernels -- the two-phase kernel (gate every
+    slot, re-deal by exact count, packed-FFMA2 walk; pairs of up to 480 correspondences) and the streaming
+    kernel (larger pairs; MV_PNP_STREAM=1 forces it for every pair) -- with 128 or 256 hypotheses per CTA:
+    same bytes for every one of 1024 hypotheses and for the selected pose.  A library built with
+    -DMV_PNP_AB adds the superseded forms (no re-deal, mask kernel, dense kernel) to the comparison."""
     import torch
+    from maveric_slam_b200 import lib
     P, H = 3, 1024
     corr = torch.from_numpy(_problems(synth, P, n, stride)).to(tracker.device)
     cnt = torch.full((P,), n, dtype=torch.int32, device=tracker.device)
-    got = {}
-    for form in ("sorted", "nosort", "mask", "dense"):
-        with _Form(form):
-            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
-            got[form] = (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes())
-    for form in ("nosort", "mask", "dense"):
-        assert got[form] == got["sorted"], form
-    # ... and the sorted kernel with 128 or 256 hypotheses per CTA (chosen by launch size otherwise)
+
+    def run():
+        pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
+        return (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes())
+
+    want = run()
     for gpw in ("1", "2"):
-        os.environ["MV_PNP_GPW"] = gpw
-        try:
-            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
-        finally:
-            del os.environ["MV_PNP_GPW"]
-        assert (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes()) == got["sorted"], gpw
-    # ... and with the re-deal (and its barriers) left out after some or all passes, so that the warps
-    # of a CTA drift apart by whole passes (n = 513 re-stages the correspondences inside every pass)
-    for mask in ("155", "00f", "000"):
-        os.environ["MV_PNP_SORTMASK"] = mask
-        try:
-            pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
-        finally:
-            del os.environ["MV_PNP_SORTMASK"]
-        assert (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes()) == got["sorted"], mask
+        with _Env("MV_PNP_GPW", gpw):
+            assert run() == want, ("two-phase", gpw)
+            with _Env("MV_PNP_STREAM", "1"):
+                assert run() == want, ("streaming", gpw)
+    if lib.load().mv_pnp_has_ab_forms():
+        for form in ("nosort", "mask", "dense"):
+            with _Env("MV_PNP_FORM", form):
+                assert run() == want, form
+        # the fused kernel with the re-deal (and its barriers) left out after some or all passes
+        for mask in ("155", "00f", "000"):
+            with _Env("MV_PNP_FORM", "fused"), _Env("MV_PNP_SORTMASK", mask):
+                assert run() == want, mask
 
 
 def test_pnp_hypothesis_does_not_depend_on_hypothesis_count(tracker, synth):
