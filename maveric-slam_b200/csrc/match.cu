@@ -169,7 +169,8 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
                     const int32_t* __restrict__ q_patch, const int32_t* __restrict__ q_idx,
                     const int32_t* __restrict__ q_count,
                     const int32_t* __restrict__ best_cell, const float* __restrict__ best_score,
-                    int n_parts, size_t part_stride, float* __restrict__ match_pts, int32_t* __restrict__ match_count,
+                    int n_parts, size_t part_stride, const int32_t* __restrict__ rank_to_cell, int rank_stride,
+                    float* __restrict__ match_pts, int32_t* __restrict__ match_count,
                     int32_t* __restrict__ match_cell0, int32_t* __restrict__ match_query,
                     float* __restrict__ match_score) {
   __shared__ int s_warp[kEmitThreads / 32];
@@ -184,7 +185,9 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
   for (int i0 = 0; i0 < nq; i0 += kEmitThreads) {
     const int i = i0 + threadIdx.x;
     // the matcher reports one candidate per part (the tcgen05 kernel: one per epilogue thread of
-    // the query's row); the winner is the larger score, ties to the earlier cell
+    // the query's row); the winner is the larger score, ties to the earlier cell.  The tcgen05 kernel
+    // reports candidates by their rank in frame 0's compacted candidate list, which is in cell order, so
+    // the tie rule is the same on ranks; rank_to_cell turns the winner back into a cell.
     int cell = -1;
     float score = 0.0f;
     if (i < nq) {
@@ -193,6 +196,7 @@ emit_matches_kernel(int rows, int cells, int top_n, int max_matches,
         const float os = best_score[part * part_stride + (size_t)pair * top_n + i];
         if (oc >= 0 && (cell < 0 || os > score || (os == score && oc < cell))) { score = os; cell = oc; }
       }
+      if (rank_to_cell && cell >= 0) cell = rank_to_cell[(size_t)f0 * rank_stride + cell];
     }
     const unsigned votes = __ballot_sync(0xffffffffu, cell >= 0);
     if (lane == 0) s_warp[wid] = __popc(votes);
@@ -242,10 +246,12 @@ extern "C" void mv_match_params_default(mv_match_params* p, int rows, int cols) 
 }
 
 int mv_match_tc_parts();
+bool mv_match_tc_feasible(const mv_match_params* p, int n_frames, int n_pairs, int top_n);
 mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs, int top_n,
                              const int32_t* d_f0, const int32_t* d_f1, const int8_t* d_desc,
                              const int32_t* d_max_idx, const float* d_prob, const int32_t* d_q_patch,
-                             const int32_t* d_q_count, int32_t* d_best_cell, float* d_best_score);
+                             const int32_t* d_q_count, int32_t* d_best_rank, float* d_best_score,
+                             const int32_t** d_rank_to_cell, int* rank_stride);
 
 extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n_frames, int n_pairs,
                                     int top_n, const int32_t* d_f0, const int32_t* d_f1,
@@ -264,7 +270,7 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
     MV_BAD_ARG(ctx, "mv_match_batch: at most 65535 pairs / frames per call (grid y dimension); split the batch");
   const int cells = p->rows * p->cols;
   int use_tc = p->use_tensor_cores;
-  if (use_tc == 2) use_tc = (p->rows <= 256 && n_frames > 0 && p->match_threshold * p->match_threshold >= 0.0) ? 1 : 0;
+  if (use_tc == 2) use_tc = mv_match_tc_feasible(p, n_frames, n_pairs, top_n) ? 1 : 0;
   const int n_parts = use_tc ? mv_match_tc_parts() : 1;
   const size_t part_stride = (size_t)n_pairs * top_n;
   void* bc = nullptr; void* bsc = nullptr;
@@ -273,12 +279,15 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
   st = mv_scratch(ctx, "match.best_score", sizeof(float) * part_stride * n_parts, &bsc);
   if (st) return st;
 
-  // 0: dp4a warp-per-query kernel; 1: tcgen05 tile kernel (error if the shape is outside its
-  // limits); 2: the tcgen05 kernel when rows <= 256 and the threshold is a number, else dp4a.
+  // 0: dp4a warp-per-query kernel; 1: tcgen05 tile kernel (MV_ERR_BAD_ARG if the shape is outside its
+  // limits); 2: the tcgen05 kernel wherever mv_match_tc_feasible() says it can run (rows <= 256, a
+  // threshold that is a number, shared memory, a driver with tensor maps), else dp4a.
   // Both produce the same bytes (tests/test_gpu_parity.py); tools/match_sweep.py times them.
+  const int32_t* rank_to_cell = nullptr;
+  int rank_stride = 0;
   if (use_tc) {
     st = mv_match_tc_launch(ctx, p, n_frames, n_pairs, top_n, d_f0, d_f1, d_desc, d_max_idx, d_prob,
-                            d_q_patch, d_q_count, (int32_t*)bc, (float*)bsc);
+                            d_q_patch, d_q_count, (int32_t*)bc, (float*)bsc, &rank_to_cell, &rank_stride);
     if (st) return st;
   } else {
     MatchGeom g;
@@ -296,8 +305,8 @@ extern "C" mv_status mv_match_batch(mv_ctx* ctx, const mv_match_params* p, int n
     mv_prof_scope ps(ctx, "emit");
     emit_matches_kernel<<<n_pairs, kEmitThreads, 0, ctx->stream>>>(
         p->rows, cells, top_n, p->max_matches, d_f0, d_f1, d_max_idx, d_q_patch, d_q_idx, d_q_count,
-        (const int32_t*)bc, (const float*)bsc, n_parts, part_stride, d_match_pts, d_match_count, d_match_cell0, d_match_query,
-        d_match_score);
+        (const int32_t*)bc, (const float*)bsc, n_parts, part_stride, rank_to_cell, rank_stride, d_match_pts,
+        d_match_count, d_match_cell0, d_match_query, d_match_score);
     MV_CHECK_LAUNCH(ctx);
   }
   return MV_OK;
