@@ -46,6 +46,14 @@ WORKLOAD = ("KITTI-00-length synthetic sequence: 4541 frames (4540 pairs), 47x15
             "r=4 window match + RANSAC-E + GN-PnP 1024 hyp x (4+10) iters")
 
 
+def workload_config(n_frames: int) -> dict:
+    """The `config` object: the workload and nothing else, identical in both arms (--impl ours | reference).
+    What is specific to an arm's run (sharding, matcher, the reference arm's sample size) goes to `run`."""
+    return {"workload": WORKLOAD, "frames": n_frames, "pairs": n_frames - 1, "grid": [ROWS, COLS], "top_n": TOP_N,
+            "max_matches": MAX_MATCHES, "hypotheses": HYPOTHESES, "gn_iters": [SAMPLE_ITERS, REFINE_ITERS],
+            "cache": "a rank's device-resident frames (10.8 GB at N=1, 1.35 GB at N=8) exceed the 126 MB L2; no flush between steps"}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -227,7 +235,9 @@ def run_reference(args, rank: int):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean([s for _, s in vals]) * 1e3), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "int8 match / fp32 PnP", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_pairs_per_step": n},
+        "config": workload_config(args.frames),
+        "run": {"sample_pairs_per_step": n, "note": "each step times the first sample_pairs_per_step pairs of the configured "
+                                                    "sequence on all host cores and reports pairs/s"},
         "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": cores, "kind": "port",
                          "sample": f"first {n} pairs of the same synthetic sequence per step, OpenMP over pairs, "
                                    "oracle/mv_oracle.c built -O3 -march=native (the reference itself is fixed at 24x80 "
@@ -335,6 +345,9 @@ def main():
     prof = {}
     for tag in ["detect", "topn", "match", "emit", "ransac", "gather", "pnp", "pnp_select"]:
         prof[tag] = tr.ctx.profile_read(tag)[0]
+    # the tensor-core matcher's three kernels (inside "match"; not added to the step sum a second time)
+    match_parts = {tag: tr.ctx.profile_read(tag)[0] for tag in ["match_compact", "match_lead", "match_gemm"]}
+    match_tiles, match_chunks = tr.ctx.match_work() if args.tensor_cores else (0, 0)
     pnp_accepted = tr.ctx.pnp_work() // 2   # accepted correspondence-passes of one step (two profiled steps)
     tr.ctx.profile(False)
 
@@ -366,44 +379,66 @@ def main():
                 "frac": ach / hbm_peak if ach else None, "ms_per_launch": ms_k, "algorithmic_bytes": bytes_,
                 "peak_source": peak_src}
 
-    # ---- matcher work: algorithmic int8 ops (2*256*sum_q |window_q|, cells valid or
-    # not) and, for the tensor-core matcher, the tile ops the tensor pipe executes (untimed pass)
+    # ---- matcher work.  Algorithmic int8 ops (2*256*sum_q |window_q|, cells valid or not) and
+    # algorithmic bytes (SURVEY §8d B_match: descriptors read once + mask/idx + output) from an untimed pass;
+    # the tile ops the tensor pipe executed from the library's own count of the chunks it ran.
     idx_t, prob_t, _ = tr.softmax(semi, scale)
     qp_t, _, _, qc_t, _ = tr.top_n(idx_t, prob_t, TOP_N, MAX_VALID)
     qp_h, qc_h = qp_t.cpu().numpy(), qc_t.cpu().numpy()
+    n_cand = int(((idx_t != 64) & ~(prob_t < 0.2)).sum().item())     # candidate cells of all frames
     del idx_t, prob_t, qp_t, qc_t
     win_cells = 0
-    tile_ops = 0
-    cx = max(1, min(256 // ROWS, COLS))
-    n_chunk = (cx * ROWS + 15) // 16 * 16
+    n_queries = 0
     for f in range(1, my_frames):
         pq = qp_h[f, :min(int(qc_h[f]), TOP_N)].astype(np.int64)
         if pq.size == 0:
             continue
+        n_queries += int(pq.size)
         x, y = pq // ROWS, pq % ROWS
         w = np.clip(np.minimum(x + 4 + 4, COLS - 1) - np.maximum(x + 4 - 4, 0) + 1, 0, None)
         h = np.clip(np.minimum(y + 4 + 4, ROWS - 1) - np.maximum(y + 4 - 4, 0) + 1, 0, None)
         win_cells += int((w * h).sum())
-        for q0 in range(0, pq.size, 128):
-            xt = x[q0:q0 + 128]
-            X0, X1 = max(int(xt.min()) + 4 - 4, 0), min(int(xt.max()) + 4 + 4, COLS - 1)
-            if X1 >= X0:
-                tile_ops += ((X1 - X0 + cx) // cx) * 2 * 128 * n_chunk * 64
     match_alg_ops = 2 * 256 * win_cells
-    int8_peak = 2.0 * (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)
-                       if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0)
-    match_ms = prof["match"]
-    if args.tensor_cores:
-        match_entry = {"kernel": "match_tc_kernel (K1, tcgen05 kind::i8 + TMA)", "bound": "tensor",
-                       "achieved": tile_ops / (match_ms * 1e-3) / 1e12 if match_ms else None, "peak": int8_peak,
-                       "unit": "TOP/s", "frac": (tile_ops / (match_ms * 1e-3) / 1e12) / int8_peak if match_ms else None,
-                       "ms_per_launch": match_ms, "executed_tile_int8_ops": tile_ops, "algorithmic_int8_ops": match_alg_ops,
-                       "algorithmic_TOPs": match_alg_ops / (match_ms * 1e-3) / 1e12 if match_ms else None,
-                       "peak_source": "2 x measured dense bf16 (MEASURED_PEAKS.json); int8 dense peak not measured by the driver",
-                       "note": "K=64 per tile (the reference scores 64 dims) and an exact-score epilogue: epilogue-bound, "
-                               "see DESIGN.md 4.1 and profiles/"}
+    tile_ops = match_chunks * 2 * 128 * 256 * 64
+    # B_match per pair = 256*(N + cells0) + 8*cells0 + 8*N + 16*matches, and the tighter figure
+    # with only the cells that are candidates (what an ideal matcher has to read under the reference's rules)
+    match_bytes_survey = 256 * (n_queries + count * cells) + 8 * count * cells + 8 * n_queries + 16 * n_corr
+    match_bytes_valid = 256 * (n_queries + n_cand) + 8 * count * cells + 8 * n_queries + 16 * n_corr
+    ipath = os.path.join(ROOT, "profiles", "int8_peak.json")
+    if os.path.exists(ipath):
+        ij = json.load(open(ipath))
+        int8_peak, int8_src = ij["int8_tops"], ("measured on this pool by tools/int8_peak.py (cuBLASLt s8 GEMM 8192^3, burst; "
+                                                "sustained %.0f): profiles/int8_peak.json" % ij["int8_tops_sustained"])
     else:
-        match_entry = None
+        int8_peak = 2.0 * (json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops", 1590.0)
+                           if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 1590.0)
+        int8_src = "ASSUMED 2 x measured dense bf16 (profiles/int8_peak.json absent)"
+    match_ms = prof["match"]
+    match_entries = []
+    if args.tensor_cores:
+        gemm_ms = match_parts["match_gemm"]
+        match_entries.append(
+            {"kernel": "match_tc_kernel (K1 tile GEMM + exact-score epilogue, tcgen05 kind::i8 + TMA)", "bound": "tensor",
+             "achieved": tile_ops / (gemm_ms * 1e-3) / 1e12 if gemm_ms else None, "peak": int8_peak, "unit": "TOP/s",
+             "frac": (tile_ops / (gemm_ms * 1e-3) / 1e12) / int8_peak if gemm_ms else None, "ms_per_launch": gemm_ms,
+             "executed_tile_int8_ops": tile_ops, "tiles": match_tiles, "chunks_128x256x64": match_chunks,
+             "algorithmic_int8_ops": match_alg_ops, "executed_over_algorithmic": tile_ops / max(1, match_alg_ops),
+             "algorithmic_TOPs_whole_matcher": match_alg_ops / (match_ms * 1e-3) / 1e12 if match_ms else None,
+             "peak_source": int8_src,
+             "note": "K=64 per tile (the reference scores 64 dims) and an exact-score epilogue: at r=4 the matcher is "
+                     "HBM/latency-bound (next entry), the tensor pipe idles; see DESIGN.md 4.1 and profiles/"})
+        match_entries.append(
+            {"kernel": "matcher K1 = compact_candidates + lead + match_tc kernels (whole)", "bound": "hbm",
+             "achieved": match_bytes_survey / (match_ms * 1e-3) / 1e9 if match_ms else None, "peak": hbm_peak, "unit": "GB/s",
+             "frac": (match_bytes_survey / (match_ms * 1e-3) / 1e9) / hbm_peak if match_ms else None,
+             "ms_per_launch": match_ms, "kernel_ms": match_parts, "algorithmic_bytes": match_bytes_survey,
+             "algorithmic_bytes_candidates_only": match_bytes_valid,
+             "frac_candidates_only": (match_bytes_valid / (match_ms * 1e-3) / 1e9) / hbm_peak if match_ms else None,
+             "peak_source": peak_src,
+             "note": "algorithmic_bytes = SURVEY §8d B_match (every cell's descriptor once); candidates_only counts the "
+                     "descriptors of candidate cells and queries only"})
+    else:
+        match_entries.append(hbm_entry("match_queries_kernel (K1a, dp4a)", "match", match_bytes_valid))
     rooflines = [
         {"kernel": ("pnp_gn_twophase_kernel (K3)" if args.lanes == 1 else "pnp_gn_kernel<%d> (K3)" % args.lanes), "bound": "fp32", "achieved": pnp_flops / (pnp_ms * 1e-3) / 1e12 if pnp_ms else None,
          "peak": fp32_nominal, "unit": "TFLOP/s",
@@ -419,11 +454,9 @@ def main():
                         "(FFMA microbenchmark on this pool: 72.9 TFLOP/s, profiles/r01/ffma_peak.txt)",
          "hbm_achieved_gbs": pnp_bytes / (pnp_ms * 1e-3) / 1e9 if pnp_ms else None},
         hbm_entry("softmax_cells_kernel (K0a)", "detect", my_frames * cells * (65 + 8)),
-        hbm_entry("top_n_kernel (K0b)", "topn", my_frames * (cells * 8 * 2 + TOP_N * 12)),
-        match_entry if match_entry else
-        hbm_entry("match_queries_kernel (K1a, dp4a)", "match",
-                  count * (256 * (TOP_N + int(0.14 * cells) * 2) + 8 * cells + 8 * TOP_N)),
-    ]
+        # K0b reads idx/prob twice (count + select); the algorithm needs them once
+        hbm_entry("top_n_kernel (K0b)", "topn", my_frames * (cells * 8 + TOP_N * 12)),
+    ] + match_entries
     step_kernel_ms = sum(v for v in prof.values())
     roofline = dict(rooflines[0])
     roofline["traffic"] = None
@@ -487,13 +520,12 @@ def main():
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "int8 match / fp32 PnP", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames": n_frames, "pairs": n_pairs, "grid": [ROWS, COLS],
-                       "top_n": TOP_N, "max_matches": MAX_MATCHES, "hypotheses": HYPOTHESES,
-                       "gn_iters": [SAMPLE_ITERS, REFINE_ITERS], "pnp_lanes_per_hypothesis": args.lanes, "matcher": "tcgen05" if args.tensor_cores else "dp4a",
-                       "match_algorithmic_int8_ops_per_step": match_alg_ops,
-                       "sharding": f"{world} x contiguous pair blocks, all_gather of 64 B/pair",
-                       "cache": f"inputs {in_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
-                       "mean_matches_per_pair": n_corr / max(1, count)},
+            "config": workload_config(n_frames),
+            "run": {"pnp_lanes_per_hypothesis": args.lanes, "matcher": "tcgen05" if args.tensor_cores else "dp4a",
+                    "match_algorithmic_int8_ops_per_step": match_alg_ops,
+                    "sharding": f"{world} x contiguous pair blocks, all_gather of 64 B/pair",
+                    "cache": f"inputs {in_bytes / 1e9:.2f} GB per rank >> 126 MB L2, no flush needed",
+                    "mean_matches_per_pair": n_corr / max(1, count)},
             "clocks": clk.summary(), "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "rooflines": rooflines, "kernel_ms": prof, "cpu_baseline": cpu,
         }

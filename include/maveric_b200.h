@@ -66,6 +66,9 @@ mv_status   mv_ctx_profile_read(mv_ctx* ctx, const char* tag, double* avg_ms, in
  * accumulated into normal equations) in the launches since the last read; the executed-work
  * figure of bench.py's roofline.  Reading resets the counter. */
 mv_status   mv_ctx_pnp_work(mv_ctx* ctx, unsigned long long* accepted);
+/* Executed work of the last tensor-core matcher launch: tiles of 128 queries that held a query, and the
+ * 128 x 256 x 64 int8 chunks the tensor pipe ran for them (blocks the call; bench.py's tensor roofline). */
+mv_status   mv_ctx_match_work(mv_ctx* ctx, unsigned long long* tiles, unsigned long long* chunks);
 
 /* ------------------------------------------------------------------------- */
 /* Detector post-processing: src/top_N.c                                      */

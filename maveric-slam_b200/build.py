@@ -22,6 +22,13 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-fmad=false", "-Xcompiler", "-fPIC,
           "-I", os.path.join(HERE, "..", "include")]
 if os.environ.get("MV_PNP_AB"):   # also compile the superseded K3 forms (A/B timing, tools/k3_ab.py)
     COMMON.append("-DMV_PNP_AB")
+# A/B builds of a tuning constant: MV_EXTRA_NVCC="-DMV_LEAD_CTAS=2" MV_OUT=/path/variant.so python build.py
+# (objects go to a directory of their own; load the variant with MV_LIB_PATH=/path/variant.so)
+if os.environ.get("MV_EXTRA_NVCC"):
+    COMMON += os.environ["MV_EXTRA_NVCC"].split()
+if os.environ.get("MV_OUT"):
+    OUT = os.path.abspath(os.environ["MV_OUT"])
+    OBJ = OUT + ".obj"
 SOURCES = ["api.cu", "detector.cu", "match.cu", "match_tc.cu", "ransac.cu", "pnp_gn.cu", "traj.cu", "nms.cu", "lba.cu", "synth.cu", "pool.cpp"]
 
 

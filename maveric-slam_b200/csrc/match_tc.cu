@@ -59,10 +59,16 @@ constexpr int kRowBytes = kTileQ * 32;          // row state of a tile
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kChunkN;
 constexpr int kEpiWarp0 = 2;
-constexpr int kEpiWarps = 16;
+#ifndef MV_TC_EPI_WARPS
+#define MV_TC_EPI_WARPS 16
+#endif
+constexpr int kEpiWarps = MV_TC_EPI_WARPS;   // 4 quadrants x kParts
 constexpr int kParts = kEpiWarps / 4;           // threads per query row, each takes every kParts-th block of 32
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
 constexpr int kLeadThreads = 4 * kTileQ;        // lead_kernel: four lanes per query
+#ifndef MV_LEAD_CTAS
+#define MV_LEAD_CTAS 3
+#endif
 constexpr int kMaxCols = 4096;
 
 struct TcGeom {
@@ -99,56 +105,63 @@ compact_candidates_kernel(TcGeom g, const int32_t* __restrict__ max_idx, const f
                           const int8_t* __restrict__ desc, uint32_t* __restrict__ vbits,
                           int32_t* __restrict__ c_cell, int32_t* __restrict__ c_col, int8_t* __restrict__ c_desc,
                           uint32_t* __restrict__ c_ytab) {
-  extern __shared__ int s_col[];   // [cols + 1]: candidates per column, then their exclusive prefix
+  extern __shared__ int s_dyn[];   // [cols + 1] candidates per column, then [vwords] validity words
   __shared__ int s_warp[8];
-  __shared__ int s_base;
+  int* s_col = s_dyn;
+  uint32_t* s_vb = reinterpret_cast<uint32_t*>(s_dyn + g.cols + 1);
   const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int i = tid; i <= g.cols; i += 256) s_col[i] = 0;
-  if (tid == 0) s_base = 0;
+  for (int i = tid; i < g.vwords; i += 256) s_vb[i] = 0;
   __syncthreads();
   const int32_t* mi = max_idx + (size_t)f * g.cells;
   const float* pr = prob + (size_t)f * g.cells;
-  uint32_t* vb = vbits + (size_t)f * g.vwords;
   int32_t* cc = c_cell + (size_t)f * g.cstride;
-  for (int c0 = 0; c0 < g.cells; c0 += 256) {
-    const int c = c0 + tid;
-    const bool v = c < g.cells && mi[c] != 64 && !(pr[c] < g.prob_lt);   // tracking_main.c:142,146
-    const unsigned votes = __ballot_sync(0xffffffffu, v);
-    if (lane == 0) {
-      vb[c >> 5] = votes;
-      s_warp[wid] = __popc(votes);
-    }
-    __syncthreads();
-    int before = s_base;
-    for (int w = 0; w < wid; w++) before += s_warp[w];
-    if (v) {
-      cc[before + __popc(votes & ((1u << lane) - 1u))] = c;
-      atomicAdd(&s_col[c / g.rows], 1);
-    }
-    __syncthreads();
-    if (tid == 0) {
-      int t = 0;
-      for (int w = 0; w < 8; w++) t += s_warp[w];
-      s_base += t;
-    }
-    __syncthreads();
+  // every thread owns a contiguous run of cells, so ranks in cell order are one block scan of the runs'
+  // counts: two passes over the run (the second one hits L1), three barriers in all
+  const int per = (g.cells + 255) >> 8;
+  const int c_lo = min(g.cells, tid * per), c_hi = min(g.cells, c_lo + per);
+  int mine = 0;
+#pragma unroll 8
+  for (int c = c_lo; c < c_hi; c++) mine += (mi[c] != 64 && !(pr[c] < g.prob_lt)) ? 1 : 0;   // tracking_main.c:142,146
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += u;
   }
-  const int count = s_base;
-  for (int w = ((g.cells + 255) >> 8 << 3) + tid; w < g.vwords; w += 256) vb[w] = 0;   // padding words
+  if (lane == 31) s_warp[wid] = incl;
+  __syncthreads();
+  int rank = incl - mine, count = 0;
+  for (int w = 0; w < 8; w++) {
+    if (w < wid) rank += s_warp[w];
+    count += s_warp[w];
+  }
+  for (int c = c_lo; c < c_hi; c++) {
+    if (mi[c] != 64 && !(pr[c] < g.prob_lt)) {
+      cc[rank++] = c;
+      atomicAdd(&s_col[c / g.rows], 1);
+      atomicOr(&s_vb[c >> 5], 1u << (c & 31));
+    }
+  }
+  __syncthreads();
+  {
+    uint32_t* vb = vbits + (size_t)f * g.vwords;
+    for (int i = tid; i < g.vwords; i += 256) vb[i] = s_vb[i];
+  }
   // exclusive prefix of the column counts (one warp, carried)
   if (wid == 0) {
     int carry = 0;
     for (int x0 = 0; x0 <= g.cols; x0 += 32) {
       const int x = x0 + lane;
       const int v = x < g.cols ? s_col[x] : 0;
-      int incl = v;
+      int in2 = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
+        const int u = __shfl_up_sync(0xffffffffu, in2, o);
+        if (lane >= o) in2 += u;
       }
-      if (x <= g.cols) c_col[(size_t)f * (g.cols + 1) + x] = carry + incl - v;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
+      if (x <= g.cols) c_col[(size_t)f * (g.cols + 1) + x] = carry + in2 - v;
+      carry += __shfl_sync(0xffffffffu, in2, 31);
     }
   }
   __syncthreads();   // the candidate list written above is read back below
@@ -156,7 +169,19 @@ compact_candidates_kernel(TcGeom g, const int32_t* __restrict__ max_idx, const f
   {
     const int4* src = reinterpret_cast<const int4*>(desc + (size_t)f * g.cells * 256);
     int4* dst = reinterpret_cast<int4*>(c_desc + (size_t)f * g.cstride * 64);
-    for (int i = tid; i < count * 4; i += 256) dst[i] = __ldg(src + (size_t)cc[i >> 2] * 16 + (i & 3));
+    // eight rows in flight per thread (the row's cell is a dependent load in front of the row itself)
+    const int total = count * 4;
+    for (int i0 = tid; i0 < total; i0 += 256 * 8) {
+      int cellv[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) cellv[u] = (i0 + 256 * u < total) ? cc[(i0 + 256 * u) >> 2] : 0;
+      int4 val[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) val[u] = __ldg(src + (size_t)cellv[u] * 16 + (tid & 3));
+#pragma unroll
+      for (int u = 0; u < 8; u++)
+        if (i0 + 256 * u < total) dst[i0 + 256 * u] = val[u];
+    }
   }
   // y table: for block b of 32 ranks and every t in [0, rows], the ranks whose cell row is >= t
   const int nb = (count + 31) >> 5;
@@ -179,10 +204,10 @@ compact_candidates_kernel(TcGeom g, const int32_t* __restrict__ max_idx, const f
 // ---------------------------------------------------------------------------------------------
 // K1q: per query the window as a rank range, the leading candidate, the later scores' constants
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int first_set_in_range(const uint32_t* __restrict__ vb, int lo, int hi) {
+__device__ __forceinline__ int first_set_in_range(const uint32_t* vb, int lo, int hi) {
   int p = lo;
   while (p <= hi) {
-    const uint32_t w = __ldg(vb + (p >> 5)) >> (p & 31);
+    const uint32_t w = vb[p >> 5] >> (p & 31);
     if (w) {
       const int q = p + __ffs(w) - 1;
       return q <= hi ? q : -1;
@@ -192,10 +217,10 @@ __device__ __forceinline__ int first_set_in_range(const uint32_t* __restrict__ v
   return -1;
 }
 // set bits in [lo, hi)
-__device__ __forceinline__ int popc_range(const uint32_t* __restrict__ vb, int lo, int hi) {
+__device__ __forceinline__ int popc_range(const uint32_t* vb, int lo, int hi) {
   int n = 0;
   for (int w = lo >> 5; (w << 5) < hi; w++) {
-    uint32_t v = __ldg(vb + w);
+    uint32_t v = vb[w];
     const int b0 = w << 5;
     if (lo > b0) v &= 0xffffffffu << (lo - b0);
     if (hi < b0 + 32) v &= (1u << (hi - b0)) - 1u;
@@ -211,12 +236,14 @@ __device__ __forceinline__ int popc_range(const uint32_t* __restrict__ vb, int l
 //   w3: brank best so far as a rank (-1: none)      w4: its score
 //   w5: den_f  float(int32(norm_F * norm_q64)), the denominator of every later score
 //   w6: curmax start of the key filter             w7: flip  0 / -1: key = n ^ flip
-__global__ void __launch_bounds__(kLeadThreads)
+__global__ void __launch_bounds__(kLeadThreads, MV_LEAD_CTAS)
 lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restrict__ f1_of,
             const int8_t* __restrict__ desc, const uint32_t* __restrict__ vbits, const int32_t* __restrict__ c_col,
             const int32_t* __restrict__ q_patch, const int32_t* __restrict__ q_count, int8_t* __restrict__ qa,
             int4* __restrict__ rowinfo, int4* __restrict__ spans) {
-  __shared__ int s_min, s_max;
+  // frame 0's validity bits and column prefix, staged once per CTA: the search below is then shared-memory
+  // lookups, and a query's chain of dependent global loads is cell -> descriptors, nothing else
+  extern __shared__ uint32_t s_tab[];            // [vwords] validity words, then [cols + 1] column prefix
   const int item = blockIdx.x;
   const int pair = item / g.tiles_per_pair;
   const int q0 = (item - pair * g.tiles_per_pair) * kTileQ;
@@ -226,47 +253,45 @@ lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restri
   const int n_rows = max(0, min(kTileQ, nq - q0));
   const int tid = threadIdx.x, lane = tid & 31, sub = tid & 3, row = tid >> 2;
   const int quad0 = lane & ~3;
-  if (tid == 0) { s_min = 0x7fffffff; s_max = 0; }
-  __syncthreads();
   const bool active = row < n_rows;
-  const uint32_t* vb = vbits + (size_t)f0 * g.vwords;
-  const int32_t* col0 = c_col + (size_t)f0 * (g.cols + 1);
+  // this thread's query: issue its loads before the tables are staged
+  int cell1 = 0;
+  if (active) cell1 = __ldg(q_patch + (size_t)f1 * g.top_n + q0 + row);
+  {
+    const uint32_t* gv = vbits + (size_t)f0 * g.vwords;
+    const int32_t* gc = c_col + (size_t)f0 * (g.cols + 1);
+    for (int i = tid; i < g.vwords; i += kLeadThreads) s_tab[i] = __ldg(gv + i);
+    for (int i = tid; i <= g.cols; i += kLeadThreads) s_tab[g.vwords + i] = (uint32_t)__ldg(gc + i);
+  }
+  const uint32_t* vb = s_tab;
+  const int32_t* col0 = reinterpret_cast<const int32_t*>(s_tab + g.vwords);
   const int8_t* d0 = desc + (size_t)f0 * g.cells * 256;
 
   int x_lo = 0, x_hi = -1, y_lo = 0, y_hi = -1;
   int4 q4[4] = {make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0), make_int4(0, 0, 0, 0)};
   if (active) {
-    const int cell1 = q_patch[(size_t)f1 * g.top_n + q0 + row];
     const int qx = cell1 / g.rows, qy = cell1 - qx * g.rows;
     x_lo = max(qx + g.shift_x - g.radius, 0);
     x_hi = min(qx + g.shift_x + g.radius, g.cols - 1);
     y_lo = max(qy + g.shift_y - g.radius, 0);
     y_hi = min(qy + g.shift_y + g.radius, g.rows - 1);
     if (y_hi < y_lo) { x_lo = 0; x_hi = -1; }
-    const int4* qp = reinterpret_cast<const int4*>(desc + ((size_t)f1 * g.cells + cell1) * 256 + sub * 64);
+    // the four lanes of a query hold the 16-byte pieces sub, sub + 4, sub + 8, sub + 12 of a descriptor:
+    // each load instruction of the quad reads 64 contiguous bytes (whole sectors)
+    const int4* qp = reinterpret_cast<const int4*>(desc + ((size_t)f1 * g.cells + cell1) * 256) + sub;
 #pragma unroll
-    for (int c = 0; c < 4; c++) q4[c] = __ldg(qp + c);
-    if (sub == 0) {   // A operand row: the first 64 bytes of the query descriptor
-      int4* dst = reinterpret_cast<int4*>(qa + ((size_t)pair * g.qstride + q0 + row) * 64);
-#pragma unroll
-      for (int c = 0; c < 4; c++) dst[c] = q4[c];
-    }
+    for (int c = 0; c < 4; c++) q4[c] = __ldg(qp + 4 * c);
   }
-  int nq_part = 0;
-#pragma unroll
-  for (int c = 0; c < 4; c++) nq_part = dp4a4(q4[c], q4[c], nq_part);
-  const int nq64 = __shfl_sync(0xffffffffu, nq_part, quad0);
-  int nq256 = nq_part;
-  nq256 += __shfl_xor_sync(0xffffffffu, nq256, 1);
-  nq256 += __shfl_xor_sync(0xffffffffu, nq256, 2);
+  __syncthreads();   // the staged tables
 
   // Leading candidates (tracking_main.c:21-32): every candidate of the window, in scan order, is scored
   // over 256 dims until one has a non-zero norm.  The four lanes of a query look at four columns at a
-  // time; the evaluation is warp-convergent, each lane on its quarter of the two descriptors.
+  // time; the evaluation is warp-convergent, each lane on its quarter of the two descriptors.  Nothing
+  // before the first candidate's loads are issued depends on the query descriptor, so the two
+  // descriptors' loads are in flight together; the query norms are taken after the loop.
   bool searching = active && x_hi >= x_lo;
   int cx = x_lo, cy = y_lo;
-  int lead_cell = -1, n_cand = 0, brank = -1;
-  float bs = 0.0f;
+  int lead_cell = -1, n_cand = 0, lead_dot = 0;
   while (__any_sync(0xffffffffu, searching)) {
     int c = -1;
     if (searching) {
@@ -282,37 +307,48 @@ lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restri
     }
     int dot = 0, nc = 0;
     if (csel >= 0) {
-      const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)csel * 256 + sub * 64);
+      const int4* cp = reinterpret_cast<const int4*>(d0 + (size_t)csel * 256) + sub;
       int4 cv[4];
 #pragma unroll
-      for (int k = 0; k < 4; k++) cv[k] = __ldg(cp + k);
+      for (int k = 0; k < 4; k++) cv[k] = __ldg(cp + 4 * k);
 #pragma unroll
       for (int k = 0; k < 4; k++) { dot = dp4a4(cv[k], q4[k], dot); nc = dp4a4(cv[k], cv[k], nc); }
     }
     dot += __shfl_xor_sync(0xffffffffu, dot, 1); nc += __shfl_xor_sync(0xffffffffu, nc, 1);
     dot += __shfl_xor_sync(0xffffffffu, dot, 2); nc += __shfl_xor_sync(0xffffffffu, nc, 2);
     if (csel >= 0) {
-      const int xs = csel / g.rows, ys = csel - xs * g.rows;
       if (nc != 0) {
-        lead_cell = csel; n_cand = nc;
-        const float s = wrapped_cos2(dot, nc, nq256);
-        if (s > g.accept_gt) { bs = s; brank = __ldg(col0 + xs) + popc_range(vb, xs * g.rows, csel); }
+        lead_cell = csel; n_cand = nc; lead_dot = dot;
         searching = false;
       } else {   // a zero descriptor scores NaN (0/0), never matches, and leaves the norm sticky
+        const int xs = csel / g.rows, ys = csel - xs * g.rows;
         cx = xs; cy = ys + 1;
         if (cy > y_hi) { cx = xs + 1; cy = y_lo; }
         searching = cx <= x_hi;
       }
     }
   }
+  // first use of the query descriptor: the A operand row (its first 64 bytes = piece 0 of every lane) and
+  // the two query norms (64 and 256 dims)
+  if (active)
+    reinterpret_cast<int4*>(qa + ((size_t)pair * g.qstride + q0 + row) * 64)[sub] = q4[0];
+  int nq64 = dp4a4(q4[0], q4[0], 0);
+  int nq256 = nq64;
+#pragma unroll
+  for (int c = 1; c < 4; c++) nq256 = dp4a4(q4[c], q4[c], nq256);
+  nq64 += __shfl_xor_sync(0xffffffffu, nq64, 1); nq256 += __shfl_xor_sync(0xffffffffu, nq256, 1);
+  nq64 += __shfl_xor_sync(0xffffffffu, nq64, 2); nq256 += __shfl_xor_sync(0xffffffffu, nq256, 2);
 
   if (sub == 0) {
-    int rlo = 0, rhi = 0, curmax = 0x7fffffff, flip = 0;
-    float den_f = 1.0f;
+    int rlo = 0, rhi = 0, curmax = 0x7fffffff, flip = 0, brank = -1;
+    float den_f = 1.0f, bs = 0.0f;
     if (lead_cell >= 0) {
       const int xs = lead_cell / g.rows;
-      rlo = __ldg(col0 + xs) + popc_range(vb, xs * g.rows, lead_cell) + 1;
-      rhi = __ldg(col0 + x_hi + 1);
+      const int lead_rank = col0[xs] + popc_range(vb, xs * g.rows, lead_cell);
+      rlo = lead_rank + 1;
+      rhi = col0[x_hi + 1];
+      const float s = wrapped_cos2(lead_dot, n_cand, nq256);
+      if (s > g.accept_gt) { bs = s; brank = lead_rank; }
       const int den_i = (int)((unsigned)n_cand * (unsigned)nq64);
       den_f = __int2float_rn(den_i);
       // conservative start of the key filter: every key <= curmax has s <= accept_gt
@@ -326,21 +362,17 @@ lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restri
       } else {
         curmax = 0;   // s = +inf only for n > 0
       }
-      if (rlo < rhi) { atomicMin(&s_min, rlo); atomicMax(&s_max, rhi); }
+      // the tile's rank span, straight into its (zeroed) span record: y = max of (INT_MAX - rlo), z = max of rhi
+      if (rlo < rhi) {
+        atomicMax(&reinterpret_cast<int*>(spans + item)[1], 0x7fffffff - rlo);
+        atomicMax(&reinterpret_cast<int*>(spans + item)[2], rhi);
+      }
     }
     int4* rdst = rowinfo + ((size_t)pair * g.qstride + q0 + row) * 2;
     rdst[0] = make_int4(rlo, rhi, (y_lo & 0xffff) | (y_hi << 16), brank);
     rdst[1] = make_int4(__float_as_int(bs), __float_as_int(den_f), curmax, flip);
   }
-  __syncthreads();
-  if (tid == 0) {
-    int r0a = 0, n_chunks = 0;
-    if (s_max > s_min) {
-      r0a = s_min & ~31;
-      n_chunks = (s_max - r0a + kChunkN - 1) / kChunkN;
-    }
-    spans[item] = make_int4(n_rows, r0a, n_chunks, 0);
-  }
+  if (tid == 0) reinterpret_cast<int*>(spans + item)[0] = n_rows;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -351,16 +383,44 @@ struct TileSpan {
   int r0a, n_chunks;          // first candidate rank (a multiple of 32), chunks of 256 ranks
 };
 
-__device__ __forceinline__ TileSpan tile_span(const TcGeom& g, int item, const int32_t* __restrict__ f0_of,
-                                              const int4* __restrict__ spans) {
-  TileSpan t;
-  t.pair = item / g.tiles_per_pair;
-  t.q0 = (item - t.pair * g.tiles_per_pair) * kTileQ;
-  t.f0 = f0_of ? f0_of[t.pair] : t.pair;
-  const int4 s = __ldg(spans + item);
-  t.n_rows = s.x; t.r0a = s.y; t.n_chunks = s.z;
-  return t;
-}
+// A role's walk over its CTA's tiles with the NEXT tile's span already in flight: the span is a global
+// load, and a role that waited for it at the top of every tile would add its latency to every tile.
+struct TileIter {
+  int item, stride, n_items;
+  int4 sp;
+  int f0;
+  __device__ __forceinline__ void fetch(const TcGeom& g, const int32_t* __restrict__ f0_of,
+                                        const int4* __restrict__ spans) {
+    sp = make_int4(0, 0, 0, 0);
+    f0 = 0;
+    if (item < n_items) {
+      sp = __ldg(spans + item);
+      const int pair = item / g.tiles_per_pair;
+      f0 = f0_of ? __ldg(f0_of + pair) : pair;
+    }
+  }
+  __device__ __forceinline__ TileSpan take(const TcGeom& g) const {
+    TileSpan t;
+    t.pair = item / g.tiles_per_pair;
+    t.q0 = (item - t.pair * g.tiles_per_pair) * kTileQ;
+    t.f0 = f0;
+    t.n_rows = sp.x;
+    const int lo = 0x7fffffff - sp.y, hi = sp.z;   // min rlo, max rhi over the tile's rows (lead_kernel)
+    t.r0a = 0; t.n_chunks = 0;
+    if (hi > lo) {
+      t.r0a = lo & ~31;
+      t.n_chunks = (hi - t.r0a + kChunkN - 1) / kChunkN;
+    }
+    return t;
+  }
+};
+#define MV_TILE_LOOP(T)                                                          \
+  TileIter it_;                                                                  \
+  it_.item = blockIdx.x; it_.stride = gridDim.x; it_.n_items = g.n_items;        \
+  it_.fetch(g, f0_of, spans);                                                    \
+  for (; it_.item < it_.n_items;)                                                \
+    if (TileSpan T = it_.take(g); true)                                          \
+      if (it_.item += it_.stride, it_.fetch(g, f0_of, spans), true)
 
 __global__ void __launch_bounds__(kThreads, 1)
 match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, TcGeom g,
@@ -403,8 +463,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     uint32_t chunk = 0, tile = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, spans);
+    MV_TILE_LOOP(t) {
       if (t.n_rows == 0) continue;
       if (lane == 0) {
         const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
@@ -431,8 +490,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     // ------------------------------------------------------------ MMA issuer
     const uint32_t idesc = umma_idesc_s8(kTileQ, kChunkN);
     uint32_t chunk = 0, tile = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, spans);
+    MV_TILE_LOOP(t) {
       if (t.n_rows == 0) continue;
       if (lane == 0) {
         const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
@@ -464,8 +522,7 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     const int part = ew >> 2;         // which of the row's kParts threads
     const int row = qd * 32 + lane;
     uint32_t chunk = 0, tile = 0;
-    for (int item = blockIdx.x; item < g.n_items; item += gridDim.x) {
-      const TileSpan t = tile_span(g, item, f0_of, spans);
+    MV_TILE_LOOP(t) {
       if (t.n_rows == 0) continue;
       const uint32_t a = tile % kAStages, aph = (tile / kAStages) & 1;
       mbar_wait(smem_u32(&bar_full_a[a]), aph, abort_flag, 6);
@@ -528,15 +585,24 @@ match_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
                 trig |= ((n > cm) != flipb) ? (1u << j) : 0u;
               }
               trig &= m;
-              // survivors (rare): exact score, in rank order, one TMEM column at a time
-              uint32_t any = __reduce_or_sync(0xffffffffu, trig);
-              while (any) {
-                const int j = __ffs(any) - 1;
-                any &= any - 1;
-                int vj;
-                tmem_ld_32x1(t_row + 32 * b + j, vj);
-                tmem_ld_wait();
-                if (trig & (1u << j)) {
+              // Survivors: exact score, in rank order.  With candidates only in a block, most rows meet
+              // their true match somewhere, so a warp-block holds a handful of survivors in different
+              // columns; each lane picks ITS next column out of its 32 registers with a five-level select
+              // tree (31 SEL for the whole warp per round, one round unless a row has several prefix maxima).
+              uint32_t rem = trig;
+              while (__any_sync(0xffffffffu, rem != 0)) {
+                const int j = rem ? __ffs(rem) - 1 : 0;
+                int s16[16], s8[8], s4[4];
+#pragma unroll
+                for (int i = 0; i < 16; i++) s16[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+#pragma unroll
+                for (int i = 0; i < 8; i++) s8[i] = (j & 2) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+                for (int i = 0; i < 4; i++) s4[i] = (j & 4) ? s8[2 * i + 1] : s8[2 * i];
+                const int s2a = (j & 8) ? s4[1] : s4[0], s2b = (j & 8) ? s4[3] : s4[2];
+                const int vj = (j & 16) ? s2b : s2a;
+                if (rem) {
+                  rem &= rem - 1;
                   const int n = (int)((unsigned)vj * (unsigned)vj);
                   const int key = n ^ flip;
                   if (key > curmax) {
@@ -583,7 +649,7 @@ static void tc_geom(const mv_match_params* p, int n_pairs, int top_n, TcGeom* g)
   g->cstride = (g->cells + 31) & ~31;
   g->nblk = g->cstride / 32;
   g->ystride = (p->rows + 1 + 3) & ~3;
-  g->vwords = ((g->cells + 255) >> 8 << 3) + 4;   // whole 256-cell trips of the compaction + padding
+  g->vwords = ((g->cells + 31) >> 5) + 4;
   g->n_items = n_pairs * g->tiles_per_pair;
   const double thr2 = p->match_threshold * p->match_threshold;
   g->accept_gt = mv_round_down(thr2);
@@ -663,13 +729,14 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   mv_prof_scope ps(ctx, "match");
   {
     mv_prof_scope p1(ctx, "match_compact");
-    compact_candidates_kernel<<<n_frames, 256, sizeof(int) * (g.cols + 1), ctx->stream>>>(
+    compact_candidates_kernel<<<n_frames, 256, sizeof(int) * (size_t)(g.cols + 1 + g.vwords), ctx->stream>>>(
         g, d_max_idx, d_prob, d_desc, (uint32_t*)vb, (int32_t*)ccell, (int32_t*)ccol, (int8_t*)cdesc, (uint32_t*)cytab);
     MV_CHECK_LAUNCH(ctx);
   }
+  MV_CUDA(ctx, cudaMemsetAsync(spans, 0, sizeof(int4) * (size_t)g.n_items, ctx->stream));
   {
     mv_prof_scope p2(ctx, "match_lead");
-    lead_kernel<<<g.n_items, kLeadThreads, 0, ctx->stream>>>(g, d_f0, d_f1, d_desc, (const uint32_t*)vb,
+    lead_kernel<<<g.n_items, kLeadThreads, sizeof(uint32_t) * (size_t)(g.vwords + g.cols + 1), ctx->stream>>>(g, d_f0, d_f1, d_desc, (const uint32_t*)vb,
                                                            (const int32_t*)ccol, d_q_patch, d_q_count, (int8_t*)qa,
                                                            (int4*)rinfo, (int4*)spans);
     MV_CHECK_LAUNCH(ctx);
@@ -686,5 +753,28 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   }
   *d_rank_to_cell = (const int32_t*)ccell;
   *rank_stride = g.cstride;
+  ctx->match_items = g.n_items;
+  return MV_OK;
+}
+
+// Executed work of the last tensor-core matcher launch on this context: tiles with at least one query and the
+// 128 x 256 x 64 chunks the tensor pipe ran for them (bench.py's `bound: tensor` roofline entry).
+extern "C" mv_status mv_ctx_match_work(mv_ctx* ctx, unsigned long long* tiles, unsigned long long* chunks) {
+  if (!tiles || !chunks) return MV_ERR_BAD_ARG;
+  MV_ENTER(ctx);
+  *tiles = *chunks = 0;
+  if (ctx->match_items <= 0) return MV_OK;
+  void* spans = nullptr;
+  mv_status st = mv_scratch(ctx, "match.tc_spans", sizeof(int4) * (size_t)ctx->match_items, &spans);
+  if (st) return st;
+  std::vector<int4> h((size_t)ctx->match_items);
+  MV_CUDA(ctx, cudaMemcpyAsync(h.data(), spans, sizeof(int4) * h.size(), cudaMemcpyDeviceToHost, ctx->stream));
+  MV_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (const int4& sp : h) {
+    if (sp.x <= 0) continue;
+    *tiles += 1;
+    const int lo = 0x7fffffff - sp.y, hi = sp.z;
+    if (hi > lo) *chunks += (unsigned long long)((hi - (lo & ~31) + kChunkN - 1) / kChunkN);
+  }
   return MV_OK;
 }

@@ -35,6 +35,7 @@ struct mv_ctx {
   unsigned long long launches = 0;
   bool profile = false;
   bool pnp_work_live = false;           // profile mode: the PnP work counter holds launches not yet read
+  int match_items = 0;                  // tiles of the last tensor-core matcher launch (mv_ctx_match_work)
   std::map<std::string, mv_prof_slot> prof;
   std::vector<mv_pending_event> pending;
 

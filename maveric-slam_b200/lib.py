@@ -11,14 +11,15 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libmaveric_b200.so")
+# MV_LIB_PATH: an A/B build of the same library (build.py MV_OUT=...); never anything but this library
+SO_PATH = os.environ.get("MV_LIB_PATH") or os.path.join(HERE, "libmaveric_b200.so")
 
 MV_OK, MV_ERR_NO_DEVICE, MV_ERR_CUDA, MV_ERR_BAD_ARG, MV_ERR_TOO_MANY_VALID = range(5)
 
 # Every symbol include/maveric_b200.h and include/maveric_slam_compat.h declare.
 NEW_SYMBOLS = [
     "mv_ctx_create", "mv_ctx_destroy", "mv_ctx_set_stream", "mv_ctx_sync", "mv_last_error", "mv_status_str",
-    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_ctx_pnp_work", "mv_pnp_has_ab_forms", "mv_softmax_batch", "mv_top_n_batch",
+    "mv_ctx_launch_count", "mv_ctx_profile", "mv_ctx_profile_read", "mv_ctx_pnp_work", "mv_ctx_match_work", "mv_pnp_has_ab_forms", "mv_softmax_batch", "mv_top_n_batch",
     "compute_softmax_ex", "compute_top_N_ex", "mv_match_params_default", "mv_match_batch",
     "mv_match_pair_host", "mv_ransac_identity_batch", "mv_pnp_params_default", "mv_pnp_gn_batch",
     "mv_build_corr_batch", "mv_track_params_default", "mv_track_sequence", "mv_track_sequence_host",
@@ -103,6 +104,7 @@ def load() -> C.CDLL:
     L.mv_ctx_profile.argtypes = [vp, i32]
     L.mv_ctx_profile_read.argtypes = [vp, C.c_char_p, C.POINTER(C.c_double), C.POINTER(i32)]
     L.mv_ctx_pnp_work.argtypes = [vp, C.POINTER(C.c_ulonglong)]
+    L.mv_ctx_match_work.argtypes = [vp, C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
     L.mv_pnp_has_ab_forms.argtypes = []
     L.mv_pnp_has_ab_forms.restype = i32
     L.mv_lba_schur_batch.argtypes = [vp, i32, i32, i32, i32, vp, vp]
@@ -196,6 +198,12 @@ class Context:
         v = C.c_ulonglong(0)
         self.check(self.lib.mv_ctx_pnp_work(self.h, C.byref(v)))
         return int(v.value)
+
+    def match_work(self):
+        """(tiles, chunks) the tensor-core matcher executed in its last launch on this context"""
+        t, c = C.c_ulonglong(0), C.c_ulonglong(0)
+        self.check(self.lib.mv_ctx_match_work(self.h, C.byref(t), C.byref(c)))
+        return int(t.value), int(c.value)
 
     def close(self) -> None:
         if getattr(self, "h", None):
