@@ -301,15 +301,15 @@ def main():
     my_frames = count + 1
     semi, desc, depth = tr.synth_frames(SEED, ROWS, COLS, first, offs[first:first + my_frames])
     scale = torch.full((my_frames,), float(synth.SEMI_SCALE), device=dev)
-    out = torch.empty((count, 64), dtype=torch.uint8, device=dev)
+    # the pack kernel writes the rank's records straight into the persistent, padded NCCL send buffer
+    gat = tracking.ResultGather(n_pairs, world, rank, dev)
+    out = gat.send
     torch.cuda.synchronize()
     in_bytes = semi.numel() + desc.numel() + depth.numel() * 4
 
     def step():
         tr.track_sequence(params, semi, scale, desc, depth, out=out)
-        if world > 1:
-            return tracking.gather_results(out, n_pairs, world)
-        return out
+        return gat.gather()
 
     def barrier():
         if world > 1:
@@ -474,6 +474,8 @@ def main():
     # ---- end to end through the host-buffer entry point
     e2e = None
     if not args.no_e2e:
+        if world > 1:   # staging memory on the NUMA node of this rank's GPU (a no-op where the platform does not say)
+            tracking.bind_to_gpu_numa_node(local_rank)
         h_semi = torch.empty(semi.shape, dtype=torch.int8, pin_memory=True)
         h_desc = torch.empty(desc.shape, dtype=torch.int8, pin_memory=True)
         h_depth = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True)
@@ -489,7 +491,8 @@ def main():
         for _ in range(args.steps):
             _, up, down = tr.track_sequence_host(params, h_semi, h_scale, h_desc, h_depth, out=h_out)
             if world > 1:
-                tracking.gather_results(torch.from_numpy(h_out.view(np.uint8).reshape(-1, 64)).to(dev), n_pairs, world)
+                gat.send.copy_(torch.from_numpy(h_out.view(np.uint8).reshape(-1, 64)), non_blocking=True)
+                gat.gather()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -458,7 +458,8 @@ def shard_pairs(n_pairs: int, world: int, rank: int):
 
 def gather_results(local, n_pairs: int, world: int, group=None):
     """all_gather of equal, padded shards of 64-byte records -> uint8 [n_pairs, 64] on every rank.
-    `local` is uint8 [count, 64] on the rank's device (NCCL) or CPU (gloo)."""
+    `local` is uint8 [count, 64] on the rank's device (NCCL) or CPU (gloo).  One-shot form (allocates and
+    copies); a loop uses :class:`ResultGather`, whose send buffer the pose kernels write straight into."""
     import torch
     import torch.distributed as dist
     per = (n_pairs + world - 1) // world
@@ -467,6 +468,32 @@ def gather_results(local, n_pairs: int, world: int, group=None):
     out = torch.empty((world * per, 64), dtype=torch.uint8, device=local.device)
     dist.all_gather_into_tensor(out, pad, group=group)
     return out[:n_pairs]
+
+
+class ResultGather:
+    """The only collective of the path: one all_gather of the 64-byte pair records, at most
+    291 KB for a KITTI-00-length sequence.  Send and receive buffers are allocated once; ``send`` -- the
+    rank's [count, 64] slice of a padded [per, 64] buffer whose padding rows stay zero -- is handed to
+    ``Tracker.track_sequence(out=...)`` / ``track_sequence_host``, so the pack kernel writes the records
+    straight into the NCCL send buffer and a step adds exactly one collective launch (no pad / zero / copy
+    kernels)."""
+
+    def __init__(self, n_pairs: int, world: int, rank: int, device, group=None):
+        import torch
+        self.n_pairs, self.world, self.group = n_pairs, world, group
+        first, count, per = shard_pairs(n_pairs, world, rank)
+        self.first, self.count, self.per = first, count, per
+        self._send = torch.zeros((per, 64), dtype=torch.uint8, device=device)
+        self.send = self._send[:count]
+        self._recv = torch.empty((world * per, 64), dtype=torch.uint8, device=device) if world > 1 else None
+
+    def gather(self):
+        """-> uint8 [n_pairs, 64] (a view of the receive buffer; valid until the next gather)."""
+        if self.world == 1:
+            return self.send
+        import torch.distributed as dist
+        dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
+        return self._recv[: self.n_pairs]
 
 
 # --------------------------------------------------------------------------------------

@@ -324,3 +324,33 @@ def test_sequence_calls_reject_nonpositive_sizes(tracker, tk, synth):
     # and the context is still usable afterwards
     res = tk.results_to_numpy(tracker.track_sequence(broken(), semi, scale, desc, depth))
     assert res.shape == (1,)
+
+
+def test_contexts_of_two_gpus_from_one_thread(synth):
+    """The device contract of maveric_b200.h: every entry point makes its context's GPU current for the call
+    and restores the caller's.  Two contexts on two GPUs used alternately from this one thread, with the
+    thread's current device left on GPU 0 throughout, return the bytes a single-GPU run returns."""
+    import torch
+    if not torch.cuda.is_available() or torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    from maveric_slam_b200 import tracking
+    rows, cols, n_frames = 24, 80, 5
+    off = synth.default_offsets(n_frames, 3)
+    outs = []
+    trackers = [tracking.Tracker(0), tracking.Tracker(1)]
+    torch.cuda.set_device(0)
+    p = tracking.track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=64)
+    data = []
+    for tr in trackers:
+        with torch.cuda.device(tr.device):
+            data.append(tr.synth_frames(3, rows, cols, 0, off))
+    torch.cuda.set_device(0)
+    for rep in range(2):
+        for tr, (semi, desc, depth) in zip(trackers, data):
+            scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tr.device)
+            assert torch.cuda.current_device() == 0
+            res = tr.track_sequence(p, semi, scale, desc, depth)
+            assert torch.cuda.current_device() == 0
+            tr.ctx.sync()
+            outs.append(res.cpu().numpy().tobytes())
+    assert len(set(outs)) == 1

@@ -44,6 +44,13 @@ def _worker(rank, world, port, n_pairs, out_dir):
     first, count, per = tracking.shard_pairs(n_pairs, world, rank)
     local = torch.from_numpy(_records(first, count).view(np.uint8).reshape(-1, 64).copy())
     full = tracking.gather_results(local, n_pairs, world)
+    # ... and the persistent form bench.py uses: records written in place into the send buffer, two steps
+    gat = tracking.ResultGather(n_pairs, world, rank, torch.device("cpu"))
+    assert (gat.first, gat.count, gat.per) == (first, count, per)
+    for step in range(2):
+        gat.send.copy_(local)
+        again = gat.gather()
+        assert again.shape == full.shape and bool((again == full).all()), step
     np.save(os.path.join(out_dir, f"rank{rank}.npy"), full.numpy())
     dist.destroy_process_group()
 

@@ -1,11 +1,13 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[4] end to end on one B200: 94x310 cells, ~12k keypoints per frame (16k
-nominal), 33x33 search window, up to 16384 matches per pair, 4096 Gauss-Newton
-hypotheses.  Device-resident frames, CUDA events, 2 warm-ups; prints one JSON line with the per-kernel
-breakdown.  Also a scale check of the whole path: two runs must return identical bytes and both
-matchers must agree.
+"""BASELINE.json configs[4] end to end: 94x310 cells, ~12k keypoints per frame (16k nominal, SURVEY §8d
+C5), 33x33 search window, up to 16384 matches per pair, 4096 Gauss-Newton hypotheses.  On one B200 or,
+under torchrun, sharded by contiguous pair blocks over N B200s with the one all_gather of 64-byte
+records (the same sharding as bench.py).  Device-resident frames, CUDA events, max over ranks, 2 warm-ups;
+prints one JSON line with the per-kernel breakdown of rank 0.  Also a scale check of the whole path: two
+runs must return identical bytes and both matchers must agree.
 
     python tools/stress_bench.py [--frames F] [--steps K]
+    python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 tools/stress_bench.py --frames 257
 """
 from __future__ import annotations
 
@@ -27,43 +29,66 @@ def main():
     import maveric_slam_b200  # noqa: F401
     from maveric_slam_b200 import synth, tracking
 
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     rows, cols, seed = 94, 310, 0
-    tr = tracking.Tracker(0)
+    n_pairs_all = args.frames - 1
+    first, count, per = tracking.shard_pairs(n_pairs_all, world, rank)
+    tr = tracking.Tracker(local_rank)
     off = synth.default_offsets(args.frames, seed)
-    semi, desc, depth = tr.synth_frames(seed, rows, cols, 0, off, keypoint_permille=550)
-    scale = torch.full((args.frames,), float(synth.SEMI_SCALE), device=tr.device)
+    semi, desc, depth = tr.synth_frames(seed, rows, cols, first, off[first:first + count + 1], keypoint_permille=550)
+    scale = torch.full((count + 1,), float(synth.SEMI_SCALE), device=tr.device)
+    gat = tracking.ResultGather(n_pairs_all, world, rank, tr.device)
 
     def params(tc=True):
         return tracking.track_params(rows, cols, top_n=16000, max_valid=32768, max_matches=16384, hypotheses=4096,
-                                     radius=16, shift=(4, 4), use_tensor_cores=tc)
+                                     radius=16, shift=(4, 4), use_tensor_cores=tc, first_pair=first)
 
     out = tr.track_sequence(params(), semi, scale, desc, depth)
     ref = out.cpu().numpy().tobytes()
     same = tr.track_sequence(params(), semi, scale, desc, depth).cpu().numpy().tobytes() == ref
     dp4a = tr.track_sequence(params(False), semi, scale, desc, depth).cpu().numpy().tobytes() == ref
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        out = tr.track_sequence(params(), semi, scale, desc, depth, out=out)
+        tr.track_sequence(params(), semi, scale, desc, depth, out=gat.send)
+        allres = gat.gather()
     e1.record()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
+    t = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=tr.device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
     tr.ctx.profile(True)
-    tr.track_sequence(params(), semi, scale, desc, depth, out=out)
+    tr.track_sequence(params(), semi, scale, desc, depth, out=gat.send)
     tr.ctx.sync()
-    prof = {t: tr.ctx.profile_read(t)[0] for t in ["detect", "topn", "match", "emit", "ransac", "gather", "pnp", "pnp_select"]}
+    prof = {t_: tr.ctx.profile_read(t_)[0] for t_ in ["detect", "topn", "match", "emit", "ransac", "gather", "pnp", "pnp_select"]}
     tr.ctx.profile(False)
+    out = allres
     res = tracking.results_to_numpy(out)
     n_pairs = args.frames - 1
-    print(json.dumps({
-        "metric": "frame-pairs/sec (window match + PnP), BASELINE configs[4] stress shape, 1 GPU",
-        "value": n_pairs / (ms * 1e-3), "unit": "frame-pairs/s", "ms_per_step": ms, "pairs": n_pairs,
-        "config": {"grid": [rows, cols], "radius": 16, "top_n": 16000, "max_matches": 16384, "hypotheses": 4096,
-                   "mean_matches_per_pair": float(res["num_matches"].mean()),
-                   "mean_pnp_inliers": float(res["pnp_inliers"].mean())},
-        "kernel_ms": prof, "deterministic": bool(same), "dp4a_matcher_same_bytes": bool(dp4a),
-        "status_ok": bool((res["status"] == 0).all())}))
+    flags = torch.tensor([int(same), int(dp4a)], device=tr.device)
+    if world > 1:
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(json.dumps({
+            "metric": "frame-pairs/sec (window match + PnP), BASELINE configs[4] stress shape, %d GPU(s)" % world,
+            "value": n_pairs / (ms * 1e-3), "unit": "frame-pairs/s", "n_gpus": world, "ms_per_step": ms, "pairs": n_pairs,
+            "config": {"grid": [rows, cols], "radius": 16, "top_n": 16000, "max_matches": 16384, "hypotheses": 4096,
+                       "mean_matches_per_pair": float(res["num_matches"].mean()),
+                       "mean_pnp_inliers": float(res["pnp_inliers"].mean())},
+            "kernel_ms_rank0": prof, "deterministic": bool(flags[0].item()), "dp4a_matcher_same_bytes": bool(flags[1].item()),
+            "status_ok": bool((res["status"] == 0).all())}))
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
