@@ -216,6 +216,49 @@ mv_status mv_build_corr_batch(mv_ctx* ctx, int n_pairs, int cells, int rows, int
                               float* d_corr);
 
 /* ------------------------------------------------------------------------- */
+/* BoW word assignment and the landmark table             */
+/* ------------------------------------------------------------------------- */
+
+/* Vocabulary of src/bow_main.c (include/data/LCD/vocabulary.h:5-272): base node descriptors int8 [256][n_base]
+ * with their scale / bias, leaf descriptors int32 [n_base][words_per_base][4].  Host pointers, copied. */
+mv_status mv_bow_set_vocabulary(mv_ctx* ctx, int n_base, int words_per_base, const int8_t* h_base_desc,
+                                const float* h_scale, const float* h_bias, const int32_t* h_leaves);
+/* Word of every query of every frame (bow_main.c:62-125 under the definition stated in csrc/bow.cu -- the
+ * reference program has no defined result, PARITY UNPINNED; its helpers get_binary_descriptor and
+ * count_matching_bits are reproduced bit for bit).
+ *   d_desc int8 [n_frames][cells][256], d_desc_scale float [n_frames], d_q_patch / d_q_count as mv_top_n_batch
+ *   d_word int32 [n_frames][top_n]  base * words_per_base + leaf, -1 beyond the frame's query count
+ *   d_base int32 [n_frames][top_n]  the selected base node (nullable)                                        */
+mv_status mv_bow_assign_batch(mv_ctx* ctx, int n_frames, int cells, int top_n, const int8_t* d_desc,
+                              const float* d_desc_scale, const int32_t* d_q_patch, const int32_t* d_q_count,
+                              int32_t* d_word, int32_t* d_base);
+
+/* The reference's LocalFeature (include/local_feature_pool.h:16-22), field for field. */
+typedef struct {
+  int word_id;        /* -1: empty */
+  int frame_ptr;
+  int num_frames;
+  int frames[8];      /* MAX_LOCAL_FRAMES ring */
+  float coords[3];    /* coords_3D */
+} mv_landmark;
+/* Device-side contents of the reference's local feature pool: a direct map word id -> LocalFeature (the host
+ * pool's hash-slot layout depends on insertion order and is not part of its contents).  d_table is caller-owned
+ * device memory of n_words records.
+ *   init        every record empty
+ *   observe     local_feature_matching.c:153-161 for one frame: insert (coords of the word's first occurrence
+ *               in the list) or update_local_feature, once per occurrence; ids outside [0, n_words) are skipped
+ *   remove_old  local_feature_pool_remove_old (:268-279): one frame older than current_frame - 7 leaves every
+ *               record, records without frames are emptied
+ *   lookup      coords_3D of a list of words (0,0,0 and found = 0 where the word is not in the table): what
+ *               supplies the 3-D side of PnP correspondences                                              */
+mv_status mv_landmarks_init(mv_ctx* ctx, int n_words, mv_landmark* d_table);
+mv_status mv_landmarks_observe(mv_ctx* ctx, int n_words, mv_landmark* d_table, int frame, int n,
+                               const int32_t* d_word_ids, const float* d_coords);
+mv_status mv_landmarks_remove_old(mv_ctx* ctx, int n_words, mv_landmark* d_table, int current_frame);
+mv_status mv_landmarks_lookup(mv_ctx* ctx, int n_words, const mv_landmark* d_table, int n,
+                              const int32_t* d_word_ids, float* d_coords, int32_t* d_found);
+
+/* ------------------------------------------------------------------------- */
 /* Whole path over a sequence of frames (pair p = frames p, p+1)              */
 /* ------------------------------------------------------------------------- */
 

@@ -26,6 +26,8 @@ NEW_SYMBOLS = [
     "mv_chain_transforms", "mv_results_to_transforms", "mv_nms_batch", "run_nms_ex", "mv_synth_frames",
     "mv_lba_schur_batch",
     "mv_lba_solve_batch",
+    "mv_bow_set_vocabulary", "mv_bow_assign_batch", "mv_landmarks_init", "mv_landmarks_observe",
+    "mv_landmarks_remove_old", "mv_landmarks_lookup",
 ]
 LEGACY_SYMBOLS = [
     "add_Vector2f", "add_Vector3f", "mult_Quaternionf", "create_Quaternionf", "Quaternionf_from_Vector3f",
@@ -128,6 +130,12 @@ def load() -> C.CDLL:
     L.mv_track_sequence.argtypes = [vp, C.POINTER(TrackParams), i32, vp, vp, vp, vp, vp]
     L.mv_track_sequence_host.argtypes = [vp, C.POINTER(TrackParams), i32, vp, vp, vp, vp, vp,
                                          C.POINTER(C.c_ulonglong), C.POINTER(C.c_ulonglong)]
+    L.mv_bow_set_vocabulary.argtypes = [vp, i32, i32, vp, vp, vp, vp]
+    L.mv_bow_assign_batch.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp, vp, vp]
+    L.mv_landmarks_init.argtypes = [vp, i32, vp]
+    L.mv_landmarks_observe.argtypes = [vp, i32, vp, i32, i32, vp, vp]
+    L.mv_landmarks_remove_old.argtypes = [vp, i32, vp, i32]
+    L.mv_landmarks_lookup.argtypes = [vp, i32, vp, i32, vp, vp, vp]
     L.mv_synth_frames.argtypes = [vp, C.POINTER(SynthParams), i32, i32, vp, vp, vp, vp]
     L.mv_nms_batch.argtypes = [vp, i32, i32, i32, vp, vp]
     L.run_nms_ex.argtypes = [vp, i32, i32, vp, vp]

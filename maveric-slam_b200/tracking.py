@@ -394,6 +394,49 @@ class Tracker:
                                                    self._d(delta), self._d(ok)))
         return delta, ok
 
+    # -- BoW word assignment and the landmark table
+    def bow_set_vocabulary(self, base_desc, scale, bias, leaves):
+        """base_desc int8 [256, n_base], scale / bias float32 [n_base], leaves int32 [n_base, wpb, 4] (host arrays)"""
+        base_desc = np.ascontiguousarray(base_desc, np.int8); scale = np.ascontiguousarray(scale, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32); leaves = np.ascontiguousarray(leaves, np.int32)
+        self.ctx.check(self.lib.mv_bow_set_vocabulary(self.ctx.h, leaves.shape[0], leaves.shape[1], _p(base_desc),
+                                                      _p(scale), _p(bias), _p(leaves)))
+        self.words_per_base = leaves.shape[1]
+        self.n_words = leaves.shape[0] * leaves.shape[1]
+
+    def bow_assign(self, desc, desc_scale, q_patch, q_count):
+        """-> (word int32 [n_frames, top_n], base int32 [n_frames, top_n]); word = base * wpb + leaf, -1 = no query"""
+        torch = self.torch
+        n, cells, _ = desc.shape
+        top_n = q_patch.shape[1]
+        word = torch.empty((n, top_n), dtype=torch.int32, device=self.device)
+        base = torch.empty((n, top_n), dtype=torch.int32, device=self.device)
+        self.ctx.check(self.lib.mv_bow_assign_batch(self.ctx.h, n, cells, top_n, self._d(desc), self._d(desc_scale),
+                                                    self._d(q_patch), self._d(q_count), self._d(word), self._d(base)))
+        return word, base
+
+    def landmarks_new(self, n_words):
+        """Empty device landmark table: uint8 [n_words, 56] (view with LANDMARK_DTYPE after .cpu().numpy())."""
+        t = self.torch.empty((n_words, 56), dtype=self.torch.uint8, device=self.device)
+        self.ctx.check(self.lib.mv_landmarks_init(self.ctx.h, n_words, self._d(t)))
+        return t
+
+    def landmarks_observe(self, table, frame, word_ids, coords=None):
+        self.ctx.check(self.lib.mv_landmarks_observe(self.ctx.h, table.shape[0], self._d(table), int(frame),
+                                                     word_ids.numel(), self._d(word_ids), self._d(coords)))
+
+    def landmarks_remove_old(self, table, current_frame):
+        self.ctx.check(self.lib.mv_landmarks_remove_old(self.ctx.h, table.shape[0], self._d(table), int(current_frame)))
+
+    def landmarks_lookup(self, table, word_ids):
+        torch = self.torch
+        n = word_ids.numel()
+        coords = torch.empty((n, 3), dtype=torch.float32, device=self.device)
+        found = torch.empty((n,), dtype=torch.int32, device=self.device)
+        self.ctx.check(self.lib.mv_landmarks_lookup(self.ctx.h, table.shape[0], self._d(table), n, self._d(word_ids),
+                                                    self._d(coords), self._d(found)))
+        return coords, found
+
     def chain_transforms(self, transforms):
         """python/compute_trajectory.py:49-51,76-77 as a parallel scan: float64 [n, 3, 4] relative
         transforms -> float64 [n+1, 3, 4] frame poses, pose 0 the identity."""
@@ -440,6 +483,10 @@ def write_trajectory(out_dir, start_frame: int, traj) -> None:
         save_pose(os.path.join(out_dir, f"frame-{start_frame + i:06d}.pose.txt"), pose)
     end = start_frame + len(traj) - 1
     write_ply(os.path.join(out_dir, f"trajectory_{start_frame:06d}_{end:06d}.ply"), [p[:3, 3] for p in traj])
+
+
+LANDMARK_DTYPE = np.dtype([("word_id", "<i4"), ("frame_ptr", "<i4"), ("num_frames", "<i4"), ("frames", "<i4", (8,)),
+                           ("coords", "<f4", (3,))])   # include/local_feature_pool.h:16-22
 
 
 def results_to_numpy(t) -> np.ndarray:

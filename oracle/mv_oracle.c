@@ -1102,6 +1102,90 @@ void orc_track_pair(const orc_track_cfg* cfg, int pair_index,
   free(pts0); free(pts1); free(cell0); free(corr); free(inl);
 }
 
+/* ------------------------------------------------------------------------------------------
+ * BoW word assignment -- src/bow_main.c:13-55 (helpers, followed line for line) and :62-125 (the stated
+ * definition of mv_oracle.h; the program itself has no defined result)
+ * ------------------------------------------------------------------------------------------ */
+void orc_bow_binarize(float scale, const int8_t* feature, int* binary8) {
+  for (int i = 0; i < 8; i++) {               /* bow_main.c:13-41 with size = 8 */
+    unsigned w = 0;
+    for (int j = 0; j < 32; j++) {
+      const int v = feature[i * 32 + j];
+      w <<= 1;
+      if (scale > 0 ? (v > 0) : (v <= 0)) w += 1;   /* :21 / :33 */
+    }
+    binary8[i] = (int)w;
+  }
+}
+
+int orc_bow_matching_bits(const int* a, const int* b, int size) {
+  int count = 0;                              /* bow_main.c:43-55: popcount of ~(a ^ b), byte by byte */
+  for (int i = 0; i < size; i++) {
+    unsigned m = ~((unsigned)a[i] ^ (unsigned)b[i]);
+    while (m) { count += (int)(m & 1u); m >>= 1; }
+  }
+  return count;
+}
+
+void orc_bow_assign(const orc_bow_vocab* v, float desc_scale, const int8_t* desc, int* base, int* wid) {
+  int sel = 0;                                /* :89 sel_base_nodes[i] = 0 */
+  float max_score = 0.0f;                     /* :91 */
+  for (int j = 0; j < v->n_base; j++) {
+    int raw = 0;
+    for (int k = 0; k < 256; k++) raw += (int)desc[k] * (int)v->base_desc[k * v->n_base + j];
+    float m = rintf(desc_scale * (float)raw * (1.0f / 256.0f));
+    if (m > 127.0f) m = 127.0f;
+    if (m < -128.0f) m = -128.0f;
+    if (m != m) m = 0.0f;
+    const float score = v->scale[j] * m + 256.0f * v->bias[j];   /* :94, unfused */
+    if (score > max_score) { max_score = score; sel = j; }       /* :96-99 */
+  }
+  int bits[8];
+  orc_bow_binarize(desc_scale, desc, bits);
+  int best_match = 0, best_wid = 0;           /* :108-109 */
+  for (int w = 0; w < v->words_per_base; w++) {
+    const int match = orc_bow_matching_bits(bits, v->leaves + ((size_t)sel * v->words_per_base + w) * 4, 8);   /* :111 */
+    if (match > best_match) { best_match = match; best_wid = w; }   /* :112-115 */
+  }
+  *base = sel;
+  *wid = best_wid;
+}
+
+/* ------------------------------------------------------------------------------------------
+ * landmark table: local_feature_pool.h:24-62 applied per word id (the hash table's slot layout is not
+ * part of the contents)
+ * ------------------------------------------------------------------------------------------ */
+void orc_pool_observe(orc_local_feature* table, int n_words, int frame, int n, const int* word_ids, const float* coords) {
+  for (int i = 0; i < n; i++) {               /* local_feature_matching.c:153-161 */
+    const int w = word_ids[i];
+    if (w < 0 || w >= n_words) continue;
+    orc_local_feature* f = &table[w];
+    if (f->word_id == -1) {                   /* inserted: init_local_feature_with_id, :31-36 */
+      f->word_id = w; f->frame_ptr = 0; f->num_frames = 1; f->frames[0] = frame;
+      for (int c = 0; c < 3; c++) f->coords[c] = coords ? coords[3 * i + c] : 0.0f;
+    } else if (f->num_frames < 8) {           /* update_local_feature, :38-48 */
+      f->frames[(f->frame_ptr + f->num_frames) % 8] = frame;
+      f->num_frames++;
+    } else {
+      f->frames[f->frame_ptr] = frame;
+      f->frame_ptr = (f->frame_ptr + 1) % 8;
+    }
+  }
+}
+
+void orc_pool_remove_old(orc_local_feature* table, int n_words, int current_frame) {
+  const int keep = current_frame - 8 + 1;     /* local_feature_pool.h:268-279 with remove_old_frame :50-62 */
+  for (int w = 0; w < n_words; w++) {
+    orc_local_feature* f = &table[w];
+    if (f->word_id == -1) continue;
+    if (f->frames[f->frame_ptr] < keep) {
+      f->frame_ptr = (f->frame_ptr + 1) % 8;
+      f->num_frames--;
+    }
+    if (f->num_frames == 0) { f->word_id = -1; f->frame_ptr = 0; f->num_frames = 0; }   /* delete_hash_entry */
+  }
+}
+
 static double now_s(void) {
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);

@@ -119,3 +119,34 @@ double orc_bench_sequence(const orc_track_cfg* cfg, const orc_synth_cfg* syn,
                           const int* offsets /*[(n+1)][2]*/, int first, int n, int threads,
                           orc_pair_result* out);
 #endif
+
+/* ---- BoW word assignment (src/bow_main.c:62-125).  PARITY UNPINNED as a whole: the
+ * reference program crashes as shipped and every stage reads memory as the wrong type (int8 arrays through
+ * the float matmul shim :81-86, an int8 row as int* :105, 8 ints of a 4-int leaf :115).  What is pinned:
+ * orc_bow_binarize / orc_bow_matching_bits equal the reference's own get_binary_descriptor (:13-41, fed the
+ * descriptor widened to int) and count_matching_bits (:43-55) bit for bit (tests/test_bow.py).  The stated
+ * definition of the rest:
+ *   raw_j   = sum_k desc[k] * base[k][j]                      int32, exact (the matmul of :81-86)
+ *   m_j     = sat_int8(rint(desc_scale * raw_j / 256))        ("mvout scale should be 1/256", int8 scores[][])
+ *   score_j = scale_arr[j] * m_j + 256 * bias_arr[j]          fp32, unfused (:94)
+ *   base    = first j whose score exceeds every earlier one and 0 (:92-101: strict >, max starts at 0, node 0)
+ *   bits    = get_binary_descriptor over the 256 elements, 8 words, MSB first (:13-41)
+ *   wid     = first leaf with the most matching bits, count_matching_bits over 8 words starting at
+ *             leaf_descriptors[base][wid][0] in the FLAT array (:110-120 reads 8 ints of a 4-int leaf, i.e.
+ *             the leaf and its successor; the 4 words after the last leaf are defined as 0)               */
+typedef struct {
+  int n_base, words_per_base;
+  const int8_t* base_desc;   /* [256][n_base]  (vocabulary.h:11) */
+  const float* scale;        /* [n_base]       (vocabulary.h:7)  */
+  const float* bias;         /* [n_base]       (vocabulary.h:9)  */
+  const int* leaves;         /* [n_base * words_per_base * 4 + 4], the last 4 zero (vocabulary.h:272) */
+} orc_bow_vocab;
+void orc_bow_binarize(float scale, const int8_t* feature, int* binary8);
+int  orc_bow_matching_bits(const int* a, const int* b, int size);
+void orc_bow_assign(const orc_bow_vocab* v, float desc_scale, const int8_t* desc, int* base, int* wid);
+
+/* ---- landmark table: the contents of the reference's local feature pool (include/local_feature_pool.h)
+ * after the per-frame sequence of local_feature_matching.c:153-163, as a map word id -> LocalFeature.  */
+typedef struct { int word_id, frame_ptr, num_frames, frames[8]; float coords[3]; } orc_local_feature;
+void orc_pool_observe(orc_local_feature* table, int n_words, int frame, int n, const int* word_ids, const float* coords);
+void orc_pool_remove_old(orc_local_feature* table, int n_words, int current_frame);

@@ -93,6 +93,16 @@ def pnp_cfg(fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, hypotheses=64, sam
                   gate_sq, min_depth, damping, seed, lanes)
 
 
+class BowVocab(C.Structure):
+    _fields_ = [("n_base", C.c_int), ("words_per_base", C.c_int), ("base_desc", C.c_void_p), ("scale", C.c_void_p),
+                ("bias", C.c_void_p), ("leaves", C.c_void_p)]
+
+
+LOCAL_FEATURE_DTYPE = np.dtype([("word_id", "<i4"), ("frame_ptr", "<i4"), ("num_frames", "<i4"), ("frames", "<i4", (8,)),
+                                ("coords", "<f4", (3,))])
+assert LOCAL_FEATURE_DTYPE.itemsize == 56   # include/local_feature_pool.h:16-22
+
+
 class Oracle:
     """T2: the parametrised restatement."""
 
@@ -131,6 +141,12 @@ class Oracle:
         L.orc_pnp_gn.argtypes = [C.POINTER(PnpCfg), C.c_int, C.c_int, C.c_int, _f32p, C.c_void_p, _f32p, _f32p, C.c_void_p]
         L.orc_synth_frame.argtypes = [C.POINTER(SynthCfg), C.c_int, C.c_int, C.c_int, _i8p, _i8p, _f32p]
         L.orc_track_pair.argtypes = [C.POINTER(TrackCfg), C.c_int, _i8p, _i8p, _f32p, _i8p, _i8p, C.POINTER(PairResult)]
+        L.orc_bow_binarize.argtypes = [C.c_float, _i8p, _i32p]
+        L.orc_bow_matching_bits.restype = C.c_int
+        L.orc_bow_matching_bits.argtypes = [_i32p, _i32p, C.c_int]
+        L.orc_bow_assign.argtypes = [C.POINTER(BowVocab), C.c_float, _i8p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.orc_pool_observe.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, _i32p, C.c_void_p]
+        L.orc_pool_remove_old.argtypes = [C.c_void_p, C.c_int, C.c_int]
         L.orc_bench_sequence.restype = C.c_double
         L.orc_bench_sequence.argtypes = [C.POINTER(TrackCfg), C.POINTER(SynthCfg), _i32p, C.c_int, C.c_int, C.c_int,
                                          C.POINTER(PairResult)]
@@ -226,6 +242,53 @@ class Oracle:
         m = np.ascontiguousarray(m, np.float32).copy()
         self.lib.orc_invert_3x3(m.reshape(-1), stride)
         return m
+
+    # -- BoW word assignment (parity unpinned as a whole; helpers pinned to bow_main.c's own functions)
+    def bow_vocab(self, base_desc, scale, bias, leaves):
+        """base_desc int8 [256, n_base], scale/bias float32 [n_base], leaves int32 [n_base, wpb, 4] -> handle"""
+        base_desc = np.ascontiguousarray(base_desc, np.int8); scale = np.ascontiguousarray(scale, np.float32)
+        bias = np.ascontiguousarray(bias, np.float32)
+        n_base, wpb = leaves.shape[0], leaves.shape[1]
+        flat = np.zeros(n_base * wpb * 4 + 4, np.int32)
+        flat[:-4] = np.ascontiguousarray(leaves, np.int32).reshape(-1)
+        v = BowVocab(n_base, wpb, base_desc.ctypes.data, scale.ctypes.data, bias.ctypes.data, flat.ctypes.data)
+        v._keep = (base_desc, scale, bias, flat)
+        return v
+
+    def bow_binarize(self, scale, feature):
+        out = np.zeros(8, np.int32)
+        self.lib.orc_bow_binarize(float(scale), np.ascontiguousarray(feature, np.int8), out)
+        return out
+
+    def bow_matching_bits(self, a, b):
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        return int(self.lib.orc_bow_matching_bits(a, b, len(a)))
+
+    def bow_assign(self, vocab, desc_scale, descs):
+        """descs int8 [n, 256] -> (base int32 [n], wid int32 [n])"""
+        descs = np.ascontiguousarray(descs, np.int8)
+        n = descs.shape[0]
+        base = np.zeros(n, np.int32); wid = np.zeros(n, np.int32)
+        b, w = C.c_int(0), C.c_int(0)
+        for i in range(n):
+            self.lib.orc_bow_assign(C.byref(vocab), float(desc_scale), descs[i], C.byref(b), C.byref(w))
+            base[i], wid[i] = b.value, w.value
+        return base, wid
+
+    # -- landmark table (contents of the reference's local feature pool)
+    def pool_new(self, n_words):
+        t = np.zeros(n_words, LOCAL_FEATURE_DTYPE)
+        t["word_id"] = -1
+        return t
+
+    def pool_observe(self, table, frame, word_ids, coords=None):
+        word_ids = np.ascontiguousarray(word_ids, np.int32)
+        c = None if coords is None else np.ascontiguousarray(coords, np.float32)
+        self.lib.orc_pool_observe(table.ctypes.data, len(table), int(frame), len(word_ids), word_ids,
+                                  None if c is None else c.ctypes.data)
+
+    def pool_remove_old(self, table, current_frame):
+        self.lib.orc_pool_remove_old(table.ctypes.data, len(table), int(current_frame))
 
     def synth_frame(self, seed, rows, cols, frame, off_x, off_y, keypoint_permille=140, noise_amp=6):
         cfg = SynthCfg(seed, rows, cols, keypoint_permille, noise_amp)
@@ -346,6 +409,43 @@ class Reference:
         self.lib.svd(*[float(v) for v in A.reshape(-1)], *[C.byref(o) for o in outs])
         vals = np.array([o.value for o in outs], np.float32)
         return vals[:9].reshape(3, 3), vals[9:18].reshape(3, 3), vals[18:].reshape(3, 3)
+
+
+def have_ref_bow() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref", "libmaveric_ref_bow.so"))
+
+
+class ReferenceBow:
+    """bow_main.c compiled by itself (oracle/Makefile): its two helper functions and the vocabulary it includes."""
+
+    def __init__(self):
+        build()
+        self.lib = C.CDLL(os.path.join(_HERE, "_ref", "libmaveric_ref_bow.so"))
+        L = self.lib
+        L.get_binary_descriptor.argtypes = [C.c_float, _i32p, _i32p, C.c_int]
+        L.count_matching_bits.restype = C.c_int
+        L.count_matching_bits.argtypes = [_i32p, _i32p, C.c_int]
+
+    def vocabulary(self):
+        """(base_desc int8 [256,10], scale f32 [10], bias f32 [10], leaves int32 [10,1000,4]) from vocabulary.h"""
+        L = self.lib
+        nb = C.c_int.in_dll(L, "num_base_nodes").value
+        wpb = C.c_int.in_dll(L, "words_per_base_node").value
+        base = np.ctypeslib.as_array((C.c_int8 * (256 * nb)).in_dll(L, "base_descriptors")).reshape(256, nb).copy()
+        scale = np.ctypeslib.as_array((C.c_float * nb).in_dll(L, "scale_arr")).copy()
+        bias = np.ctypeslib.as_array((C.c_float * nb).in_dll(L, "bias_arr")).copy()
+        leaves = np.ctypeslib.as_array((C.c_int * (nb * wpb * 4)).in_dll(L, "leaf_descriptors")).reshape(nb, wpb, 4).copy()
+        return base, scale, bias, leaves
+
+    def get_binary_descriptor(self, scale, feature_int32, size=8):
+        f = np.ascontiguousarray(feature_int32, np.int32)
+        out = np.zeros(size, np.int32)
+        self.lib.get_binary_descriptor(float(scale), f, out, size)
+        return out
+
+    def count_matching_bits(self, a, b):
+        a = np.ascontiguousarray(a, np.int32); b = np.ascontiguousarray(b, np.int32)
+        return int(self.lib.count_matching_bits(a, b, len(a)))
 
 
 def lba_reference_factors(flat=None, n_ldmks=1000, n_poses=8, chunk=4):
