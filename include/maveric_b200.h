@@ -257,6 +257,17 @@ mv_status mv_landmarks_observe(mv_ctx* ctx, int n_words, mv_landmark* d_table, i
 mv_status mv_landmarks_remove_old(mv_ctx* ctx, int n_words, mv_landmark* d_table, int current_frame);
 mv_status mv_landmarks_lookup(mv_ctx* ctx, int n_words, const mv_landmark* d_table, int n,
                               const int32_t* d_word_ids, float* d_coords, int32_t* d_found);
+/* Matches -> PnP correspondences with the 3-D side from the landmark table instead of a depth map (the
+ * lookup local_feature_pool.h:16-22 `coords_3D` exists for): match j of pair p -> its frame-0 cell -> that
+ * cell's place in frame 0's query list -> its word (mv_bow_assign_batch) -> table[word].coords.  A match
+ * without a landmark gets NaN coordinates (never accepted by the Gauss-Newton gate); lists keep order and
+ * length.  Same d_corr layout as mv_build_corr_batch; d_n_with_landmark int32 [n_pairs] (nullable). */
+mv_status mv_build_corr_landmarks_batch(mv_ctx* ctx, int n_pairs, int top_n, int stride, int n_words,
+                                        const mv_landmark* d_table, const int32_t* d_f0,
+                                        const int32_t* d_q_patch, const int32_t* d_q_count,
+                                        const int32_t* d_word, const float* d_match_pts,
+                                        const int32_t* d_match_count, const int32_t* d_match_cell0,
+                                        float* d_corr, int32_t* d_n_with_landmark);
 
 /* ------------------------------------------------------------------------- */
 /* Whole path over a sequence of frames (pair p = frames p, p+1)              */

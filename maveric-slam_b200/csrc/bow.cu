@@ -205,7 +205,64 @@ __global__ void landmarks_lookup_kernel(int n_words, const mv_landmark* __restri
   if (found) found[i] = ok ? 1 : 0;
 }
 
+// Matches -> PnP correspondences whose 3-D side comes from the landmark table (local_feature_pool.h:16-22
+// `coords_3D`): the matched frame-0 cell is looked up in frame 0's query list (ascending cells: binary search),
+// its word in the table.  A match whose cell is no query of frame 0, or whose word has no landmark, gets NaN
+// coordinates: the Gauss-Newton gate never accepts it, the correspondence lists keep their order and length.
+__global__ void build_corr_landmarks_kernel(int n_words, const mv_landmark* __restrict__ table, int top_n, int stride,
+                                            const int32_t* __restrict__ f0_of, const int32_t* __restrict__ q_patch,
+                                            const int32_t* __restrict__ q_count, const int32_t* __restrict__ word,
+                                            const float* __restrict__ match_pts, const int32_t* __restrict__ match_count,
+                                            const int32_t* __restrict__ match_cell0, float* __restrict__ corr,
+                                            int32_t* __restrict__ n_with_landmark) {
+  const int pair = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= match_count[pair]) return;
+  const int f0 = f0_of ? f0_of[pair] : pair;
+  const int cell = match_cell0[(size_t)pair * stride + j];
+  const int32_t* qp = q_patch + (size_t)f0 * top_n;
+  int lo = 0, hi = min(q_count[f0], top_n);
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (qp[mid] < cell) lo = mid + 1; else hi = mid;
+  }
+  const float qnan = __int_as_float(0x7fc00000);
+  float X = qnan, Y = qnan, Z = qnan;
+  if (lo < min(q_count[f0], top_n) && qp[lo] == cell) {
+    const int w = word[(size_t)f0 * top_n + lo];
+    if (w >= 0 && w < n_words && table[w].word_id == w) {
+      X = table[w].coords[0]; Y = table[w].coords[1]; Z = table[w].coords[2];
+      if (n_with_landmark) atomicAdd(&n_with_landmark[pair], 1);
+    }
+  }
+  const float4 m = reinterpret_cast<const float4*>(match_pts)[(size_t)pair * stride + j];
+  float* o = corr + (size_t)pair * 5 * stride;
+  o[j] = X; o[stride + j] = Y; o[2 * stride + j] = Z;
+  o[3 * stride + j] = m.z;
+  o[4 * stride + j] = m.w;
+}
+
 }  // namespace
+
+extern "C" mv_status mv_build_corr_landmarks_batch(mv_ctx* ctx, int n_pairs, int top_n, int stride, int n_words,
+                                                   const mv_landmark* d_table, const int32_t* d_f0,
+                                                   const int32_t* d_q_patch, const int32_t* d_q_count,
+                                                   const int32_t* d_word, const float* d_match_pts,
+                                                   const int32_t* d_match_count, const int32_t* d_match_cell0,
+                                                   float* d_corr, int32_t* d_n_with_landmark) {
+  MV_ENTER(ctx);
+  if (n_pairs <= 0 || n_pairs > 65535 || top_n <= 0 || stride <= 0 || n_words <= 0 || !d_table || !d_q_patch || !d_q_count ||
+      !d_word || !d_match_pts || !d_match_count || !d_match_cell0 || !d_corr)
+    MV_BAD_ARG(ctx, "mv_build_corr_landmarks_batch");
+  if (d_n_with_landmark) MV_CUDA(ctx, cudaMemsetAsync(d_n_with_landmark, 0, sizeof(int32_t) * (size_t)n_pairs, ctx->stream));
+  mv_prof_scope ps(ctx, "gather");
+  dim3 grid((stride + 127) / 128, n_pairs);
+  build_corr_landmarks_kernel<<<grid, 128, 0, ctx->stream>>>(n_words, d_table, top_n, stride, d_f0, d_q_patch, d_q_count,
+                                                            d_word, d_match_pts, d_match_count, d_match_cell0, d_corr,
+                                                            d_n_with_landmark);
+  MV_CHECK_LAUNCH(ctx);
+  return MV_OK;
+}
 
 extern "C" mv_status mv_bow_set_vocabulary(mv_ctx* ctx, int n_base, int words_per_base, const int8_t* h_base_desc,
                                            const float* h_scale, const float* h_bias, const int32_t* h_leaves) {

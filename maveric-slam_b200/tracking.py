@@ -437,6 +437,18 @@ class Tracker:
                                                     self._d(coords), self._d(found)))
         return coords, found
 
+    def build_corr_landmarks(self, table, pts, cnt, cell0, q_patch, q_count, word, f0=None):
+        """Correspondences [n_pairs, 5, M] whose 3-D side is the landmark of the matched frame-0 keypoint's word
+        (NaN where there is none) -> (corr, n_with_landmark int32 [n_pairs])."""
+        torch = self.torch
+        n_pairs, M, _ = pts.shape
+        corr = torch.zeros((n_pairs, 5, M), dtype=torch.float32, device=self.device)
+        nl = torch.zeros((n_pairs,), dtype=torch.int32, device=self.device)
+        self.ctx.check(self.lib.mv_build_corr_landmarks_batch(
+            self.ctx.h, n_pairs, q_patch.shape[1], M, table.shape[0], self._d(table), self._d(f0), self._d(q_patch),
+            self._d(q_count), self._d(word), self._d(pts), self._d(cnt), self._d(cell0), self._d(corr), self._d(nl)))
+        return corr, nl
+
     def chain_transforms(self, transforms):
         """python/compute_trajectory.py:49-51,76-77 as a parallel scan: float64 [n, 3, 4] relative
         transforms -> float64 [n+1, 3, 4] frame poses, pose 0 the identity."""

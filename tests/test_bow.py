@@ -247,3 +247,72 @@ def test_gpu_landmark_table_equals_pool_contents(tracker, oracle):
         tracker.landmarks_remove_old(t2, f)
         got = t2.cpu().numpy().view(tracking.LANDMARK_DTYPE).reshape(-1)
         assert table_contents(got) == table_contents(o2), f
+
+
+@pytest.mark.gpu
+def test_gpu_landmarks_supply_the_3d_side_of_pnp(tracker, oracle, synth, vocab_np):
+    """The loop SURVEY §8f rank 3 closes: queries -> words -> landmark table -> coords_3D of the matched frame-0
+    keypoints -> Gauss-Newton PnP.  The landmarks of frame f are its query keypoints back-projected with the frame's
+    depth (the same fp32 operations as mv_build_corr_batch).  Where the matched frame-0 keypoint is a query of its
+    frame and the first keypoint of its word, the landmark correspondence equals the depth correspondence bit for
+    bit; elsewhere it is NaN (no landmark) or another keypoint's landmark (a word collision, an outlier to the
+    solver); the pose solved from the landmark correspondences agrees with the depth-based one."""
+    import torch
+    from maveric_slam_b200 import tracking
+    rows, cols, n_frames, N, M = 47, 155, 3, 1000, 1024
+    base_desc, scale, bias, leaves = vocab_np
+    tracker.bow_set_vocabulary(base_desc, scale, bias, leaves)
+    off = synth.default_offsets(n_frames, 5)
+    semi, desc, depth = tracker.synth_frames(5, rows, cols, 0, off)
+    sscale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+    idx, prob, _ = tracker.softmax(semi, sscale)
+    qp, qi, _, qc, _ = tracker.top_n(idx, prob, N, 8192)
+    dscale = torch.full((n_frames,), 4.3353, device=tracker.device)
+    word, _ = tracker.bow_assign(desc, dscale, qp, qc)
+    p = tracking.kitti_track_params()
+    pts, cnt, cell0, _, _ = tracker.match(p.match, desc, idx, prob, qp, qi, qc)
+    cam = (p.pnp.fx, p.pnp.fy, p.pnp.cx, p.pnp.cy)
+    corr_d = tracker.build_corr(pts, cnt, cell0, depth, cam, rows)
+    hq, hi_, hc, hw, hz = (t.cpu().numpy() for t in (qp, qi, qc, word, depth))
+    f32 = np.float32
+    poses = []
+    for pair in range(n_frames - 1):
+        f0 = pair
+        k = int(hc[f0])
+        cells = hq[f0, :k]
+        x = (cells // rows * 8 + hi_[f0, :k] % 8).astype(f32)
+        y = (cells % rows * 8 + hi_[f0, :k] // 8).astype(f32)
+        dz = hz[f0, cells]
+        coords = np.stack([(x - f32(cam[2])) / f32(cam[0]) * dz, (y - f32(cam[3])) / f32(cam[1]) * dz, dz], 1).astype(f32)
+        table = tracker.landmarks_new(10000)
+        tracker.landmarks_observe(table, f0, torch.from_numpy(hw[f0, :k].copy()).to(tracker.device),
+                                  torch.from_numpy(coords).to(tracker.device))
+        corr_l, nl = tracker.build_corr_landmarks(table, pts[pair:pair + 1], cnt[pair:pair + 1], cell0[pair:pair + 1], qp, qc,
+                                                  word, f0=torch.tensor([f0], dtype=torch.int32, device=tracker.device))
+        n = int(cnt[pair])
+        cl, cd, c0 = corr_l[0].cpu().numpy(), corr_d[pair].cpu().numpy(), cell0[pair].cpu().numpy()
+        assert (cl[3:, :n].view(np.int32) == cd[3:, :n].view(np.int32)).all()     # the 2-D side is the match
+        first_of_word = {}
+        for q in range(k):
+            first_of_word.setdefault(int(hw[f0, q]), q)
+        exact = nan = other = 0
+        for j in range(n):
+            q = int(np.searchsorted(cells, c0[j]))
+            if q >= k or cells[q] != c0[j]:
+                assert np.isnan(cl[:3, j]).all()
+                nan += 1
+            elif first_of_word[int(hw[f0, q])] == q:
+                assert (cl[:3, j].view(np.int32) == cd[:3, j].view(np.int32)).all(), (pair, j)
+                exact += 1
+            else:
+                assert (cl[:3, j].view(np.int32) == coords[first_of_word[int(hw[f0, q])]].view(np.int32)).all()
+                other += 1
+        assert int(nl[0]) == exact + other and exact > 0.5 * n, (exact, other, nan, n)
+        pose_l, stats_l, _ = tracker.pnp_gn(p.pnp, corr_l, cnt[pair:pair + 1])
+        pose_d, stats_d, _ = tracker.pnp_gn(p.pnp, corr_d[pair:pair + 1].contiguous(), cnt[pair:pair + 1])
+        pl, pd = pose_l.cpu().numpy()[0], pose_d.cpu().numpy()[0]
+        ang = 2 * np.arccos(min(1.0, abs(float(np.dot(pl[:4], pd[:4]))) / (np.linalg.norm(pl[:4]) * np.linalg.norm(pd[:4]))))
+        # (a sanity bound: the two solves see different correspondence subsets -- word collisions are outliers here)
+        assert stats_l.cpu().numpy()[0, 3] == 1 and ang < 5e-3 and np.linalg.norm(pl[4:] - pd[4:]) < 0.3, (ang, pl, pd)
+        assert stats_l.cpu().numpy()[0, 0] >= 0.3 * stats_d.cpu().numpy()[0, 0]
+        poses.append(ang)
