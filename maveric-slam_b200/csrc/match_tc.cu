@@ -65,10 +65,15 @@ constexpr int kEpiWarp0 = 2;
 constexpr int kEpiWarps = MV_TC_EPI_WARPS;   // 4 quadrants x kParts
 constexpr int kParts = kEpiWarps / 4;           // threads per query row, each takes every kParts-th block of 32
 constexpr int kThreads = 32 * (kEpiWarp0 + kEpiWarps);
-constexpr int kLeadThreads = 4 * kTileQ;        // lead_kernel: four lanes per query
-#ifndef MV_LEAD_CTAS
-#define MV_LEAD_CTAS 3
+#ifndef MV_LEAD_Q
+#define MV_LEAD_Q 32                             // queries per lead_kernel CTA (a divisor of the tile's 128; measured 0.509 / 0.512 / 0.530 ms at 32 / 64 / 128)
 #endif
+#ifndef MV_LEAD_CTAS
+#define MV_LEAD_CTAS (3 * 128 / MV_LEAD_Q)
+#endif
+constexpr int kLeadQ = MV_LEAD_Q;
+constexpr int kLeadParts = kTileQ / kLeadQ;     // CTAs per tile
+constexpr int kLeadThreads = 4 * kLeadQ;        // lead_kernel: four lanes per query
 constexpr int kMaxCols = 4096;
 
 struct TcGeom {
@@ -121,8 +126,13 @@ compact_candidates_kernel(TcGeom g, const int32_t* __restrict__ max_idx, const f
   const int per = (g.cells + 255) >> 8;
   const int c_lo = min(g.cells, tid * per), c_hi = min(g.cells, c_lo + per);
   int mine = 0;
+  unsigned flags = 0;   // the run's verdicts, kept when the run fits a word (no second read of idx / prob)
 #pragma unroll 8
-  for (int c = c_lo; c < c_hi; c++) mine += (mi[c] != 64 && !(pr[c] < g.prob_lt)) ? 1 : 0;   // tracking_main.c:142,146
+  for (int c = c_lo; c < c_hi; c++) {
+    const bool v = mi[c] != 64 && !(pr[c] < g.prob_lt);   // tracking_main.c:142,146
+    mine += v ? 1 : 0;
+    flags |= (v ? 1u : 0u) << ((c - c_lo) & 31);
+  }
   int incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -137,7 +147,8 @@ compact_candidates_kernel(TcGeom g, const int32_t* __restrict__ max_idx, const f
     count += s_warp[w];
   }
   for (int c = c_lo; c < c_hi; c++) {
-    if (mi[c] != 64 && !(pr[c] < g.prob_lt)) {
+    const bool v = per <= 32 ? ((flags >> (c - c_lo)) & 1u) != 0 : (mi[c] != 64 && !(pr[c] < g.prob_lt));
+    if (v) {
       cc[rank++] = c;
       atomicAdd(&s_col[c / g.rows], 1);
       atomicOr(&s_vb[c >> 5], 1u << (c & 31));
@@ -244,14 +255,14 @@ lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restri
   // frame 0's validity bits and column prefix, staged once per CTA: the search below is then shared-memory
   // lookups, and a query's chain of dependent global loads is cell -> descriptors, nothing else
   extern __shared__ uint32_t s_tab[];            // [vwords] validity words, then [cols + 1] column prefix
-  const int item = blockIdx.x;
+  const int item = blockIdx.x / kLeadParts, part = blockIdx.x - item * kLeadParts;
   const int pair = item / g.tiles_per_pair;
   const int q0 = (item - pair * g.tiles_per_pair) * kTileQ;
   const int f0 = f0_of ? f0_of[pair] : pair;
   const int f1 = f1_of ? f1_of[pair] : pair + 1;
   const int nq = min(q_count[f1], g.top_n);
   const int n_rows = max(0, min(kTileQ, nq - q0));
-  const int tid = threadIdx.x, lane = tid & 31, sub = tid & 3, row = tid >> 2;
+  const int tid = threadIdx.x, lane = tid & 31, sub = tid & 3, row = part * kLeadQ + (tid >> 2);
   const int quad0 = lane & ~3;
   const bool active = row < n_rows;
   // this thread's query: issue its loads before the tables are staged
@@ -372,7 +383,7 @@ lead_kernel(TcGeom g, const int32_t* __restrict__ f0_of, const int32_t* __restri
     rdst[0] = make_int4(rlo, rhi, (y_lo & 0xffff) | (y_hi << 16), brank);
     rdst[1] = make_int4(__float_as_int(bs), __float_as_int(den_f), curmax, flip);
   }
-  if (tid == 0) reinterpret_cast<int*>(spans + item)[0] = n_rows;
+  if (tid == 0 && part == 0) reinterpret_cast<int*>(spans + item)[0] = n_rows;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -736,7 +747,7 @@ mv_status mv_match_tc_launch(mv_ctx* ctx, const mv_match_params* p, int n_frames
   MV_CUDA(ctx, cudaMemsetAsync(spans, 0, sizeof(int4) * (size_t)g.n_items, ctx->stream));
   {
     mv_prof_scope p2(ctx, "match_lead");
-    lead_kernel<<<g.n_items, kLeadThreads, sizeof(uint32_t) * (size_t)(g.vwords + g.cols + 1), ctx->stream>>>(g, d_f0, d_f1, d_desc, (const uint32_t*)vb,
+    lead_kernel<<<g.n_items * kLeadParts, kLeadThreads, sizeof(uint32_t) * (size_t)(g.vwords + g.cols + 1), ctx->stream>>>(g, d_f0, d_f1, d_desc, (const uint32_t*)vb,
                                                            (const int32_t*)ccol, d_q_patch, d_q_count, (int8_t*)qa,
                                                            (int4*)rinfo, (int4*)spans);
     MV_CHECK_LAUNCH(ctx);
