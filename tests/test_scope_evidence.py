@@ -1,6 +1,7 @@
-"""Evidence for a scope decision, kept runnable: DESIGN.md section 7 leaves SURVEY section 8(f) rank 3's BoW word
-assignment unbuilt because the reference's program for it (src/bow_main.c) has no result to be faithful
-to.  This compiles that program from the reference's own sources (the two files of its CMake target,
+"""Evidence kept runnable: the reference's BoW program (src/bow_main.c) has no result to be faithful to, which is
+why the word assignment of SURVEY section 8(f) rank 3 is built on a STATED definition (DESIGN.md section 4.6,
+csrc/bow.cu) with only its two helper functions and its vocabulary pinned to the reference (tests/test_bow.py).
+This compiles that program from the reference's own sources (the two files of its CMake target,
 CMakeLists.txt:19-21, no build system) and shows that it dies with SIGSEGV before printing a word, at
 every optimisation level -- its int8 arrays go to the float* matmul shim and to int* readers
 (bow_main.c:81-86, :105, :115).  Needs /root/reference, so it runs in the build container only."""

@@ -27,7 +27,7 @@ scale = torch.full((nf,), float(synth.SEMI_SCALE), device=tr.device)
 if "seq" in stages:
     ref = None
     for tc in (True, False):
-        for lanes, hyp in ((1, 300), (2, 128), (8, 64), (32, 32)):
+        for lanes, hyp in ((1, 300), (32, 32)):     # the product's two K3 mappings (2..16 lanes: -DMV_PNP_AB builds)
             p = tracking.track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=hyp,
                                       lanes=lanes, use_tensor_cores=tc)
             res = tr.track_sequence(p, semi, scale, desc, depth)
@@ -36,11 +36,11 @@ if "seq" in stages:
                 b = res.cpu().numpy().tobytes()
                 ref = ref or b
                 assert b == ref, "matchers disagree"
-    for form in ("nosort", "mask", "dense"):
-        os.environ["MV_PNP_FORM"] = form
+    for knob in ("MV_PNP_STREAM", "MV_PNP_GPW"):     # streaming kernel for every pair; 128 hypotheses per CTA
+        os.environ[knob] = "1"
         p = tracking.track_params(rows, cols, top_n=100, max_valid=1000, max_matches=150, hypotheses=300)
-        assert tr.track_sequence(p, semi, scale, desc, depth).cpu().numpy().tobytes() == ref, form
-    os.environ.pop("MV_PNP_FORM")
+        assert tr.track_sequence(p, semi, scale, desc, depth).cpu().numpy().tobytes() == ref, knob
+        os.environ.pop(knob)
     # KITTI grid: ragged tiles of 128 queries, windows clipped at the border
     s2, d2, z2 = tr.synth_frames(2, 47, 155, 0, synth.default_offsets(3, 2))
     p = tracking.kitti_track_params(hypotheses=256)
