@@ -354,3 +354,48 @@ def test_contexts_of_two_gpus_from_one_thread(synth):
             tr.ctx.sync()
             outs.append(res.cpu().numpy().tobytes())
     assert len(set(outs)) == 1
+
+
+def test_matchers_agree_on_random_shapes(tracker, synth):
+    """Differential test of the compacted tcgen05 matcher against the dp4a kernel (itself held to the oracle shape by
+    shape in test_gpu_parity.py) on 24 random configurations: odd grids (1-row, 1-column, 255 rows), windows of
+    radius 0 ... larger than the grid, shifts that push windows off the grid, query counts around the 128-query
+    tile and the match cap, densities from a handful of candidates to every cell, batches in which some frames have
+    no keypoint at all, and explicit (f0, f1) pair lists that reuse frames.  Matches, counts, cells, queries and
+    score bits must be identical."""
+    import torch
+    from maveric_slam_b200 import tracking
+    rng = np.random.default_rng(77)
+    for trial in range(24):
+        rows = int(rng.choice([1, 2, 3, 7, 24, 47, 64, 255]))
+        cols = int(rng.choice([1, 2, 5, 33, 80, 155])) if rows > 3 else int(rng.choice([40, 200, 700]))
+        cells = rows * cols
+        permille = int(rng.choice([5, 60, 140, 550, 1000]))
+        N = int(rng.choice([1, 7, 127, 128, 129, 300, 1000]))
+        M = int(rng.choice([1, 16, 150, 1024]))
+        radius = int(rng.choice([0, 1, 4, 9, 40]))
+        shift = (int(rng.integers(-6, 7)), int(rng.integers(-6, 7)))
+        n_frames = int(rng.integers(2, 6))
+        off = synth.default_offsets(n_frames, 100 + trial)
+        semi, desc, _ = tracker.synth_frames(100 + trial, rows, cols, 0, off, keypoint_permille=permille)
+        if trial % 4 == 1:
+            semi[int(rng.integers(0, n_frames))] = -100          # a frame without keypoints
+        scale = torch.full((n_frames,), float(synth.SEMI_SCALE), device=tracker.device)
+        idx, prob, _ = tracker.softmax(semi, scale)
+        qp, qi, _, qc, _ = tracker.top_n(idx, prob, N, cells + 1)
+        f0 = f1 = None
+        if trial % 3 == 2:                                       # explicit pairs, frames reused, a frame with itself
+            pairs = [(int(rng.integers(0, n_frames)), int(rng.integers(0, n_frames))) for _ in range(5)]
+            f0 = torch.tensor([a for a, _ in pairs], dtype=torch.int32, device=tracker.device)
+            f1 = torch.tensor([b for _, b in pairs], dtype=torch.int32, device=tracker.device)
+        outs = []
+        for tc in (False, True):
+            p = tracking.match_params(rows, cols, shift[0], shift[1], radius, M, use_tensor_cores=tc)
+            res = tracker.match(p, desc, idx, prob, qp, qi, qc, f0=f0, f1=f1)
+            cnt = res[1].cpu().numpy()
+            rec = [cnt.tobytes()]
+            for t in (res[0], res[2], res[3], res[4]):            # points, cell0, query, score: the first cnt entries
+                a = t.cpu().numpy()
+                rec.append(b"".join(a[i, :cnt[i]].tobytes() for i in range(len(cnt))))
+            outs.append(rec)
+        assert outs[0] == outs[1], (trial, rows, cols, permille, N, M, radius, shift)
