@@ -476,34 +476,101 @@ def main():
     if not args.no_e2e:
         if world > 1:   # staging memory on the NUMA node of this rank's GPU (a no-op where the platform does not say)
             tracking.bind_to_gpu_numa_node(local_rank)
-        h_semi = torch.empty(semi.shape, dtype=torch.int8, pin_memory=True)
-        h_desc = torch.empty(desc.shape, dtype=torch.int8, pin_memory=True)
-        h_depth = torch.empty(depth.shape, dtype=torch.float32, pin_memory=True)
-        h_scale = torch.empty(scale.shape, dtype=torch.float32, pin_memory=True)
-        h_semi.copy_(semi); h_desc.copy_(desc); h_depth.copy_(depth); h_scale.copy_(scale)
-        torch.cuda.synchronize()
-        h_out = np.zeros(count, tracking.PAIR_RESULT_DTYPE)
-        up = down = 0
-        for _ in range(2):
-            _, up, down = tr.track_sequence_host(params, h_semi, h_scale, h_desc, h_depth, out=h_out)
+        res_device = res.clone()   # all pairs, as the device-resident steps gathered them
+
+        class HostShard:
+            """Pinned host copies of frames [first_, first_ + count_] and the parameters of that block."""
+            def __init__(self, first_, count_):
+                self.first, self.count = first_, count_
+                if (first_, count_) == (first, count):
+                    s_, d_, z_ = semi, desc, depth
+                else:
+                    s_, d_, z_ = tr.synth_frames(SEED, ROWS, COLS, first_, offs[first_:first_ + count_ + 1])
+                self.semi = torch.empty(s_.shape, dtype=torch.int8, pin_memory=True)
+                self.desc = torch.empty(d_.shape, dtype=torch.int8, pin_memory=True)
+                self.depth = torch.empty(z_.shape, dtype=torch.float32, pin_memory=True)
+                self.scale = torch.full((count_ + 1,), float(synth.SEMI_SCALE), dtype=torch.float32).pin_memory()
+                self.semi.copy_(s_); self.desc.copy_(d_); self.depth.copy_(z_)
+                torch.cuda.synchronize()
+                self.params = params if first_ == first else tracking.kitti_track_params(
+                    top_n=TOP_N, max_valid=MAX_VALID, max_matches=MAX_MATCHES, hypotheses=HYPOTHESES,
+                    refine_iters=REFINE_ITERS, sample_iters=SAMPLE_ITERS, seed=SEED, first_pair=first_,
+                    lanes=args.lanes, use_tensor_cores=args.tensor_cores)
+                self.out = np.zeros(count_, tracking.PAIR_RESULT_DTYPE)
+                self.up = self.down = 0
+
+            def run(self):
+                if self.count > 0:
+                    _, self.up, self.down = tr.track_sequence_host(self.params, self.semi, self.scale, self.desc,
+                                                                   self.depth, out=self.out)
+
+        def all_ranks(x: float):
+            v = torch.full((world,), 0.0, dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_gather_into_tensor(v, torch.tensor([x], dtype=torch.float64, device=dev))
+            else:
+                v[0] = x
+            return [float(a) for a in v.tolist()]
+
+        # Blocks of the host-buffer path follow the ranks' measured step times (tracking.balance_shards): on a
+        # box whose GPUs do not share one host-link rate, equal blocks leave the fast ranks idle.  At most three
+        # rounds of: every rank runs its block at the same time, times are gathered, blocks are re-cut.  Symmetric
+        # boxes (and N = 1) keep the equal blocks.  MV_BENCH_BALANCE=0 switches it off, MV_BENCH_WEIGHTS=a,b,..
+        # forces a partition (test hook).
+        counts = [tracking.shard_pairs(n_pairs, world, r)[1] for r in range(world)]
+        equal_counts = list(counts)
+        balance_log = []
+        forced = os.environ.get("MV_BENCH_WEIGHTS")
+        if world > 1 and forced:
+            counts = [c for _, c in tracking.shard_pairs_weighted(n_pairs, [float(x) for x in forced.split(",")])]
+        shard = HostShard(sum(counts[:rank]), counts[rank])
+        shard.run()
+        shard.run()
+        if world > 1 and not forced and os.environ.get("MV_BENCH_BALANCE", "1") != "0":
+            for _ in range(3):
+                best = float("inf")
+                for _ in range(2):
+                    barrier()
+                    t0 = time.perf_counter()
+                    shard.run()
+                    best = min(best, time.perf_counter() - t0)
+                secs = all_ranks(best)
+                balance_log.append({"pairs_per_rank": list(counts), "rank_ms": [round(x * 1e3, 3) for x in secs]})
+                new_counts = tracking.balance_shards(counts, secs)
+                if new_counts == counts:
+                    break
+                counts = new_counts
+                shard = HostShard(sum(counts[:rank]), counts[rank])
+                shard.run()
+        gat_e = gat if counts == equal_counts else tracking.ResultGather(n_pairs, world, rank, dev, counts=counts)
         barrier()
         t0 = time.perf_counter()
+        full = None
         for _ in range(args.steps):
-            _, up, down = tr.track_sequence_host(params, h_semi, h_scale, h_desc, h_depth, out=h_out)
+            shard.run()
             if world > 1:
-                gat.send.copy_(torch.from_numpy(h_out.view(np.uint8).reshape(-1, 64)), non_blocking=True)
-                gat.gather()
+                gat_e.send.copy_(torch.from_numpy(shard.out.view(np.uint8).reshape(-1, 64)), non_blocking=True)
+                full = gat_e.gather()
         barrier()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item()) / args.steps
-        same = h_out.tobytes() == resn.tobytes()
-        e2e = {"value": n_pairs / e2e_s, "unit": "frame-pairs/s", "h2d_bytes_per_step": int(up),
-               "d2h_bytes_per_step": int(down), "ms_per_step": e2e_s * 1e3, "results_equal_device_path": bool(same),
-               "api": "mv_track_sequence_host (pinned host buffers, chunked H2D overlapped with compute)"}
-        del h_semi, h_desc, h_depth
+        up_all, down_all = sum(all_ranks(float(shard.up))), sum(all_ranks(float(shard.down)))
+        if world > 1:
+            same = bool(torch.equal(full, res_device))
+        else:
+            same = shard.out.tobytes() == resn.tobytes()
+        e2e = {"value": n_pairs / e2e_s, "unit": "frame-pairs/s",
+               "h2d_bytes_per_step": int(up_all), "d2h_bytes_per_step": int(down_all),
+               "bytes_are": "summed over the ranks", "ms_per_step": e2e_s * 1e3,
+               "results_equal_device_path": bool(same),
+               "api": "mv_track_sequence_host (pinned host buffers, chunked H2D overlapped with compute)",
+               "pairs_per_rank": list(counts)}
+        if balance_log:
+            e2e["balance_rounds"] = balance_log
+        del shard
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

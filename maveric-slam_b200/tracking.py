@@ -515,6 +515,43 @@ def shard_pairs(n_pairs: int, world: int, rank: int):
     return first, max(0, min(n_pairs, first + per) - first), per
 
 
+def shard_pairs_weighted(n_pairs: int, weights):
+    """Contiguous blocks sized in proportion to `weights` (one per rank) -> [(first, count), ...].
+
+    For the host-buffer path, whose step time is the host link's: on a box where the GPUs do not all see the
+    same host-to-device rate (measured on the 8 x B200 pool box: 23 GB/s on GPUs 0-3, 35 GB/s on GPUs 4-7 with
+    all eight copying), equal blocks leave the fast ranks idle for a third of the step.  Counts are rounded by
+    largest remainder, so they always sum to n_pairs; blocks stay contiguous (pose chaining stays local)."""
+    w = [max(0.0, float(x)) for x in weights]
+    tot = sum(w)
+    if not w or tot <= 0.0:
+        raise ValueError("shard_pairs_weighted: weights must hold a positive entry")
+    exact = [n_pairs * x / tot for x in w]
+    counts = [int(e) for e in exact]
+    by_remainder = sorted(range(len(w)), key=lambda r: (exact[r] - counts[r], -r), reverse=True)
+    for r in by_remainder[: n_pairs - sum(counts)]:
+        counts[r] += 1
+    out, first = [], 0
+    for cnt in counts:
+        out.append((first, cnt))
+        first += cnt
+    return out
+
+
+def balance_shards(counts, seconds, tolerance: float = 0.10):
+    """New per-rank pair counts from one measured step: `counts[r]` pairs took rank r `seconds[r]`.
+    Returns `counts` unchanged when the slowest and fastest rank are within `tolerance` of each other
+    (symmetric boxes: no churn from timing noise)."""
+    live = [(c, s) for c, s in zip(counts, seconds) if c > 0 and s > 0.0]
+    if len(live) < 2:
+        return list(counts)
+    t = [s for _, s in live]
+    if max(t) <= (1.0 + tolerance) * min(t):
+        return list(counts)
+    rates = [c / s if (c > 0 and s > 0.0) else 0.0 for c, s in zip(counts, seconds)]
+    return [cnt for _, cnt in shard_pairs_weighted(sum(counts), rates)]
+
+
 def gather_results(local, n_pairs: int, world: int, group=None):
     """all_gather of equal, padded shards of 64-byte records -> uint8 [n_pairs, 64] on every rank.
     `local` is uint8 [count, 64] on the rank's device (NCCL) or CPU (gloo).  One-shot form (allocates and
@@ -537,22 +574,38 @@ class ResultGather:
     straight into the NCCL send buffer and a step adds exactly one collective launch (no pad / zero / copy
     kernels)."""
 
-    def __init__(self, n_pairs: int, world: int, rank: int, device, group=None):
+    def __init__(self, n_pairs: int, world: int, rank: int, device, group=None, counts=None):
+        """`counts`: pairs per rank of a weighted partition (:func:`shard_pairs_weighted`); default: the
+        equal blocks of :func:`shard_pairs`."""
         import torch
         self.n_pairs, self.world, self.group = n_pairs, world, group
-        first, count, per = shard_pairs(n_pairs, world, rank)
+        self._rows = None
+        if counts is None:
+            first, count, per = shard_pairs(n_pairs, world, rank)
+        else:
+            if len(counts) != world or sum(counts) != n_pairs or min(counts) < 0:
+                raise ValueError("ResultGather: counts must hold one entry per rank and sum to n_pairs")
+            first, count, per = sum(counts[:rank]), counts[rank], max(1, max(counts))
+            if world > 1:   # where each pair's record lands in the padded receive buffer
+                self._rows = torch.cat([torch.arange(r * per, r * per + c, dtype=torch.int64)
+                                        for r, c in enumerate(counts)]).to(device)
+                self._out = torch.empty((n_pairs, 64), dtype=torch.uint8, device=device)
         self.first, self.count, self.per = first, count, per
         self._send = torch.zeros((per, 64), dtype=torch.uint8, device=device)
         self.send = self._send[:count]
         self._recv = torch.empty((world * per, 64), dtype=torch.uint8, device=device) if world > 1 else None
 
     def gather(self):
-        """-> uint8 [n_pairs, 64] (a view of the receive buffer; valid until the next gather)."""
+        """-> uint8 [n_pairs, 64] (a view of a buffer this object owns; valid until the next gather)."""
         if self.world == 1:
             return self.send
+        import torch
         import torch.distributed as dist
         dist.all_gather_into_tensor(self._recv, self._send, group=self.group)
-        return self._recv[: self.n_pairs]
+        if self._rows is None:
+            return self._recv[: self.n_pairs]
+        torch.index_select(self._recv, 0, self._rows, out=self._out)   # unequal blocks: drop the padding rows
+        return self._out
 
 
 # --------------------------------------------------------------------------------------
