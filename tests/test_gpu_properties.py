@@ -197,12 +197,14 @@ def test_sequence_full_config_properties(tracker, tk, synth):
     assert host.tobytes() == full.tobytes() and down == 64 * (n_frames - 1)
     # selective staging moves the logits, the depth and only the descriptor rows the matcher reads
     assert up < semi.numel() + 4 * depth.numel() + desc.numel() // 2
-    os.environ["MV_HOST_CHUNK_PAIRS"] = "7"
-    try:
-        chunked, _, _ = tracker.track_sequence_host(params(), hs, hsc, hd, hz)
-    finally:
-        del os.environ["MV_HOST_CHUNK_PAIRS"]
-    assert chunked.tobytes() == full.tobytes()
+    # the chunk size of the staging pipeline must not change a byte (7: a last chunk of 5 pairs; 40: 40 + 40 + 16)
+    for chunk_pairs in ("7", "40"):
+        os.environ["MV_HOST_CHUNK_PAIRS"] = chunk_pairs
+        try:
+            chunked, _, _ = tracker.track_sequence_host(params(), hs, hsc, hd, hz)
+        finally:
+            del os.environ["MV_HOST_CHUNK_PAIRS"]
+        assert chunked.tobytes() == full.tobytes(), chunk_pairs
 
 
 def test_trajectory_chain_is_associative(tracker, tk):
