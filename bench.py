@@ -14,6 +14,9 @@ in contiguous blocks (strong scaling) and only the 64-byte per-pair results are 
 `value`  : device-resident inputs, CUDA-event timed, max over ranks.
 `e2e`    : the same work through mv_track_sequence_host with pinned HOST buffers: per step all
            frames go host->device (chunked, overlapped with compute) and results come back.
+           At N > 1 the ranks' blocks of this leg are cut by measured rank time before the timed
+           steps (tracking.balance_shards: the host links of a box need not be equal); the gathered
+           records are compared with the device-resident step's.
 `roofline`: the dominant kernel (Gauss-Newton PnP; FP32-issue bound) plus
            `rooflines` for every kernel of the step against its own bound.
 `cpu_baseline`: the CPU port of the same path (oracle/, -O3 -march=native, OpenMP) on a bounded
