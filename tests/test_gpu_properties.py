@@ -89,6 +89,31 @@ def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
                 assert run() == want, mask
 
 
+def test_pnp_split_launch_returns_identical_bytes(tracker, synth):
+    """How K3 cuts a batch into CTAs does not change a byte: 128-hypothesis CTAs for every pair (short
+    launches), 256-hypothesis CTAs for every pair, or the split launch (the shortest pairs of the
+    longest-first order as 128-hypothesis CTAs on a second stream) -- on a batch whose pairs differ in
+    length, with empty pairs and pairs long enough for the streaming kernel."""
+    import torch
+    P, stride, H = 11, 1024, 1024
+    counts = [330, 5, 0, 480, 600, 17, 330, 1000, 128, 3, 250]
+    corr = torch.from_numpy(_problems(synth, P, 1000, stride)).to(tracker.device)
+    cnt = torch.tensor(counts, dtype=torch.int32, device=tracker.device)
+
+    def run():
+        pose, stats, hyp = tracker.pnp_gn(_pnp_params(H), corr, cnt, want_hyp=True)
+        return (pose.cpu().numpy().tobytes(), stats.cpu().numpy().tobytes(), hyp.cpu().numpy().tobytes())
+
+    want = run()                                   # 11 pairs: every pair as 128-hypothesis CTAs
+    with _Env("MV_PNP_K3_SMALL_BELOW", "0"):       # never the short-launch form
+        assert run() == want, "split launch, 5 tail pairs"
+        for tail in ("0", "1", "3"):
+            with _Env("MV_PNP_TAIL_PAIRS", tail):
+                assert run() == want, ("tail pairs", tail)
+        with _Env("MV_PNP_ORDER", "0"):            # index order: no split
+            assert run() == want, "index order"
+
+
 def test_pnp_hypothesis_does_not_depend_on_hypothesis_count(tracker, synth):
     """configs[4]: 4096 hypotheses.  Hypothesis h is a function of (seed, pair, h) alone, so the first
     1024 of a 4096-hypothesis run are the 1024-hypothesis run, bit for bit, and the selected pose is
