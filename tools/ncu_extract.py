@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Condenses Nsight Compute reports into the small text files kept under profiles/.
 
-    python tools/ncu_extract.py raw   <report.ncu-rep> <out.csv>     selected metrics, one row per metric
+    python tools/ncu_extract.py raw   <report.ncu-rep> <out.csv> [i]  selected metrics, one row per metric (kernel i of the report; default: the last)
     python tools/ncu_extract.py hot   <report.ncu-rep> <out.txt> [N] stall totals + N hottest SASS lines
     python tools/ncu_extract.py launches <launches.csv> <out.txt>    per-kernel launch count / time / share
 """
@@ -33,9 +33,9 @@ def ncu_csv(rep, page):
     return list(csv.reader(io.StringIO(out)))
 
 
-def raw(rep, dst):
+def raw(rep, dst, which=-1):
     rows = ncu_csv(rep, "raw")
-    hdr, units, vals = rows[0], rows[1], rows[-1]
+    hdr, units, vals = rows[0], rows[1], (rows[2:])[which]
     with open(dst, "w") as f:
         f.write("metric,unit,value\n")
         for k in ("Kernel Name", "Block Size", "Grid Size"):
@@ -99,7 +99,7 @@ def launches(src, dst):
 if __name__ == "__main__":
     cmd = sys.argv[1]
     if cmd == "raw":
-        raw(sys.argv[2], sys.argv[3])
+        raw(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else -1)
     elif cmd == "hot":
         hot(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 25)
     elif cmd == "launches":
