@@ -8,6 +8,7 @@ with the default's.
     K3_AB_TAG=match python tools/k3_ab.py                 (another kernel's time; K3_AB_FRAMES=569 a shorter sequence)
     MV_LIB_PATH=/path/variant.so python tools/k3_ab.py    (an A/B build of the library: build.py MV_EXTRA_NVCC / MV_OUT)
 """
+import hashlib
 import json
 import os
 import sys
@@ -47,4 +48,5 @@ for env in variants:
     b = res.cpu().numpy().tobytes()
     if ref is None:
         ref = b
-    print(json.dumps({"env": env, TAG + "_ms": ms, "same_bytes": b == ref}), flush=True)
+    print(json.dumps({"env": env, TAG + "_ms": ms, "same_bytes": b == ref, "sha1": hashlib.sha1(b).hexdigest()[:12]}),
+          flush=True)   # sha1: compare two libraries (MV_LIB_PATH) across processes
