@@ -75,9 +75,6 @@ extern "C" void mv_ctx_destroy(mv_ctx* c) {
   cudaStreamSynchronize(c->stream);
   cudaStreamSynchronize(c->copy_stream);
   cudaStreamSynchronize(c->gather_stream);
-  if (c->tail_stream) { cudaStreamSynchronize(c->tail_stream); cudaStreamDestroy(c->tail_stream); }
-  if (c->tail_fork) cudaEventDestroy(c->tail_fork);
-  if (c->tail_join) cudaEventDestroy(c->tail_join);
   for (auto& ev : c->pending) { cudaEventDestroy(ev.beg); cudaEventDestroy(ev.end); }
   for (auto& kv : c->scratch) cudaFree(kv.second.first);
   if (c->pinned) cudaFreeHost(c->pinned);

@@ -31,9 +31,6 @@ struct mv_ctx {
   cudaStream_t copy_stream = nullptr; // host-buffer sequence call: logits DMA + detector (high priority)
   cudaStream_t gather_stream = nullptr; // host-buffer sequence call: selective descriptor staging
   int pnp_max_ctas_per_sm = 0;        // >0: cap K3 residency so staging kernels can co-reside
-  // K3's shortest pairs run as half-size CTAs beside the main launch (pnp_gn.cu); created on first use
-  cudaStream_t tail_stream = nullptr;
-  cudaEvent_t tail_fork = nullptr, tail_join = nullptr;
   char err[512] = {0};
   unsigned long long launches = 0;
   bool profile = false;

@@ -92,7 +92,7 @@ def test_pnp_forms_return_identical_bytes(tracker, synth, n, stride):
 def test_pnp_split_launch_returns_identical_bytes(tracker, synth):
     """How K3 cuts a batch into CTAs does not change a byte: 128-hypothesis CTAs for every pair (short
     launches), 256-hypothesis CTAs for every pair, or the split launch (the shortest pairs of the
-    longest-first order as 128-hypothesis CTAs on a second stream) -- on a batch whose pairs differ in
+    longest-first order as 128-hypothesis CTAs in a programmatic dependent launch) -- on a batch whose pairs differ in
     length, with empty pairs and pairs long enough for the streaming kernel."""
     import torch
     P, stride, H = 11, 1024, 1024
