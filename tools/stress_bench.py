@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""BASELINE.json configs[4] end to end: 94x310 cells, ~12k keypoints per frame (16k nominal, SURVEY §8d
-C5), 33x33 search window, up to 16384 matches per pair, 4096 Gauss-Newton hypotheses.  On one B200 or,
+"""BASELINE.json configs[4] end to end: 94x310 cells, 16k keypoints per frame (--permille 850:
+85 % of the synthetic world's cells are keypoints, of which the detector selects the top 16 000 per frame;
+round 1 and the first half of round 2 ran --permille 550 = ~12.2k keypoints), 33x33 search window, up to 16384 matches per pair, 4096 Gauss-Newton hypotheses.  On one B200 or,
 under torchrun, sharded by contiguous pair blocks over N B200s with the one all_gather of 64-byte
 records (the same sharding as bench.py).  Device-resident frames, CUDA events, max over ranks, 2 warm-ups;
 prints one JSON line with the per-kernel breakdown of rank 0.  Also a scale check of the whole path: two
@@ -24,6 +25,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=33)
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--permille", type=int, default=850, help="keypoint density of the synthetic world")
     args = ap.parse_args()
     import torch
     import maveric_slam_b200  # noqa: F401
@@ -41,7 +43,7 @@ def main():
     first, count, per = tracking.shard_pairs(n_pairs_all, world, rank)
     tr = tracking.Tracker(local_rank)
     off = synth.default_offsets(args.frames, seed)
-    semi, desc, depth = tr.synth_frames(seed, rows, cols, first, off[first:first + count + 1], keypoint_permille=550)
+    semi, desc, depth = tr.synth_frames(seed, rows, cols, first, off[first:first + count + 1], keypoint_permille=args.permille)
     scale = torch.full((count + 1,), float(synth.SEMI_SCALE), device=tr.device)
     gat = tracking.ResultGather(n_pairs_all, world, rank, tr.device)
 
@@ -74,6 +76,8 @@ def main():
     tr.ctx.profile(False)
     out = allres
     res = tracking.results_to_numpy(out)
+    idx_, prob_, _ = tr.softmax(semi, scale)
+    kp = float(tr.top_n(idx_, prob_, 16000, 32768)[3].float().mean().item())   # query keypoints per frame (rank 0)
     n_pairs = args.frames - 1
     flags = torch.tensor([int(same), int(dp4a)], device=tr.device)
     if world > 1:
@@ -83,6 +87,7 @@ def main():
             "metric": "frame-pairs/sec (window match + PnP), BASELINE configs[4] stress shape, %d GPU(s)" % world,
             "value": n_pairs / (ms * 1e-3), "unit": "frame-pairs/s", "n_gpus": world, "ms_per_step": ms, "pairs": n_pairs,
             "config": {"grid": [rows, cols], "radius": 16, "top_n": 16000, "max_matches": 16384, "hypotheses": 4096,
+                       "keypoint_permille": args.permille, "keypoints_per_frame": kp,
                        "mean_matches_per_pair": float(res["num_matches"].mean()),
                        "mean_pnp_inliers": float(res["pnp_inliers"].mean())},
             "kernel_ms_rank0": prof, "deterministic": bool(flags[0].item()), "dp4a_matcher_same_bytes": bool(flags[1].item()),
