@@ -95,6 +95,22 @@ def main():
                     "pairs_per_s": n_pairs / (ms * 1e-3), "matches_per_pair": out[m][2] / n_pairs,
                     "algorithmic_int8_ops": a_ops, "algorithmic_TOPS": a_ops / (ms * 1e-3) / 1e12,
                     "descriptor_bytes": int(desc.numel())}
+            if m == "tc":   # what the tensor pipe executed (128 x 256 x 64 chunks) and the tile kernel's own time
+                tiles, chunks = tr.ctx.match_work()
+                tr.ctx.profile(True)
+                tr.match(p, desc, idx, prob, qp, qi, qc)
+                tr.ctx.sync()
+                parts = {t_: tr.ctx.profile_read(t_)[0] for t_ in ("match_compact", "match_lead", "match_gemm")}
+                tr.ctx.profile(False)
+                tile_ops = chunks * 2 * 128 * 256 * 64
+                line.update({"executed_tile_int8_ops": tile_ops, "executed_over_algorithmic": tile_ops / a_ops,
+                             "kernel_ms": parts,
+                             "tile_kernel_TOPS": tile_ops / (parts["match_gemm"] * 1e-3) / 1e12 if parts["match_gemm"] else None})
+                try:
+                    peak = json.load(open(os.path.join(ROOT, "profiles", "int8_peak.json")))["int8_tops"]
+                    line["tile_kernel_frac_of_measured_int8_peak"] = line["tile_kernel_TOPS"] / peak
+                except Exception:
+                    pass
             print(json.dumps(line), flush=True)
         if len(out) == 2:
             same = out["dp4a"][1] == out["tc"][1]
